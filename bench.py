@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fused fwd+bwd disorder-sampled SU(2) propagation + fidelity loss.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl uqoc|reference] [--workload curriculum|grape]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): SU(2) propagations/s, fwd+bwd; 1 propagation = one (pulse, error sample)
+pair, a step over B targets x M samples x L pulses is B*M*L propagations.
+
+Workloads
+  curriculum (default): BASELINE config 5 slice -- B=4096 targets x L=256 x M=4096 Philox samples per
+      target PER GPU (the full config has 10^6 samples/target sharded over 8 GPUs = 131072 per GPU,
+      minutes per step; this is a time-bounded slice of the same shape, weak scaling in the sample
+      axis exactly like the full config).  One step = fused kernel + (N>1) one NCCL all-reduce of
+      [Fsum | dSumF/dpulses] + loss finalize.
+  grape: BASELINE config 3 -- B=1, L=256, M=65536 explicit eps per GPU.
+
+One JSON line on stdout (rank 0).  `value` = device-resident whole-job throughput; `e2e` = the
+same step through the public API with HOST buffers (pinned H2D of pulses/targets, D2H of loss and
+gradient inside the timed region); `roofline` = the fused kernel against the FP32 FMA pipe;
+`cpu_baseline` = the reference's CPU implementation (oracle/torch_port.py, same ATen op sequence)
+on this host's cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PROP_FWDBWD = 116.0   # 35 forward + 81 backward, algorithmic
+
+
+# ------------------------------------------------------------------------------------ workloads
+def make_workload(name: str, device, seed: int = 0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if name == "curriculum":
+        B, L, M = 4096, 256, 4096
+        tau_lo, tau_hi = 0.1, 0.5            # train/unitary_single_qubit_gate/model_params.json:4-5
+        explicit = False
+    elif name == "grape":
+        B, L, M = 1, 256, 65536
+        tau_lo, tau_hi = 0.035, 0.07         # train/GRAPE/model_params.json:4
+        explicit = True
+    else:
+        raise ValueError(name)
+    phi = (torch.rand(B, L, generator=g) * 2 - 1) * 3.15
+    tau = tau_lo + (tau_hi - tau_lo) * torch.rand(B, L, generator=g)
+    pulses = torch.stack([phi, tau], -1).contiguous()
+    # random SU(2) targets, as build_SU2_dataset(random=True) (SCORE.py:215-251)
+    th = torch.rand(B, generator=g) * math.pi
+    ph = torch.rand(B, generator=g) * 2 * math.pi
+    al = torch.rand(B, generator=g) * 2 * math.pi
+    n = torch.stack([th.sin() * ph.cos(), th.sin() * ph.sin(), th.cos()], 1)
+    c, s = (al / 2).cos(), (al / 2).sin()
+    U = torch.zeros(B, 2, 2, dtype=torch.complex64)
+    U[:, 0, 0] = torch.complex(c, -s * n[:, 2])
+    U[:, 0, 1] = torch.complex(-s * n[:, 1], -s * n[:, 0])
+    U[:, 1, 0] = torch.complex(s * n[:, 1], -s * n[:, 0])
+    U[:, 1, 1] = torch.complex(c, s * n[:, 2])
+    return dict(name=name, B=B, L=L, M=M, pulses=pulses, U_target=U, explicit=explicit, sigma=(1.0, 0.05))
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        # "under load" = samples above half the max clock (idle samples before/after the region dropped)
+        load = [x for x in sm if mx and x > 0.5 * mx] or sm
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(workload_name: str, L: int, budget_s: float = 12.0):
+    """Reference CPU path (torch port, all host threads) on a bounded sample of the workload."""
+    from oracle import torch_port as tp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    B, M = 1, 4096
+    phi = (torch.rand(B, L, generator=g) * 2 - 1) * 3.15
+    tau = 0.1 + 0.4 * torch.rand(B, L, generator=g)
+    pulses = torch.stack([phi, tau], -1)
+    T = torch.eye(2, dtype=torch.complex64)[None]
+    err = torch.stack([torch.randn(B * M, generator=g), 0.05 * torch.randn(B * M, generator=g)])
+    tp.train_step_loss_and_grad(pulses, T, err, M)      # warm-up
+    best, reps, t_all = float("inf"), 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t_all < budget_s and reps < 10):
+        t0 = time.perf_counter()
+        tp.train_step_loss_and_grad(pulses, T, err, M)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    props = B * M * L
+    return {"value": props / best, "unit": "prop/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"B={B} target x M={M} samples x L={L} (complex64, tree product, sharp_loss, autograd backward), "
+                      f"best of {reps} after warm-up; host has {os.cpu_count()} logical cores"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = {"curriculum": (4096, 256, 4096), "grape": (1, 256, 65536)}[args.workload]
+    L = wl[1]
+    from oracle import torch_port as tp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    B, M = 1, 2048        # bounded sample of the workload per step
+    phi = (torch.rand(B, L, generator=g) * 2 - 1) * 3.15
+    tau = 0.1 + 0.4 * torch.rand(B, L, generator=g)
+    pulses = torch.stack([phi, tau], -1)
+    T = torch.eye(2, dtype=torch.complex64)[None]
+    err = torch.stack([torch.randn(B * M, generator=g), 0.05 * torch.randn(B * M, generator=g)])
+    for _ in range(max(1, min(args.warmup, 3))):
+        tp.train_step_loss_and_grad(pulses, T, err, M)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tp.train_step_loss_and_grad(pulses, T, err, M)
+    dt = (time.perf_counter() - t0) / steps
+    val = B * M * L / dt
+    sample = (f"per step B={B} x M={M} samples x L={L} of workload '{args.workload}' (complex64, tree product, "
+              f"sharp_loss, autograd), {steps} steps")
+    print(json.dumps({
+        "impl": "reference", "metric": "SU(2) propagations/s fwd+bwd", "value": val, "unit": "prop/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "L": L, "note": "CPU reference path (torch port of the reference op sequence)"},
+        "cpu_baseline": {"value": val, "unit": "prop/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "prop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="uqoc", choices=["uqoc", "reference"])
+    ap.add_argument("--workload", default="curriculum", choices=["curriculum", "grape"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--fast-sincos", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="tuning flags (tuning_flags())")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the uqoc ops have no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    import universal_quantum_optimal_control_b200 as uq
+    from universal_quantum_optimal_control_b200 import ops
+
+    rdt = torch.float32 if args.dtype == "f32" else torch.float64
+    wl = make_workload(args.workload, dev)
+    B, L, M = wl["B"], wl["L"], wl["M"]
+    M_total = M * world                                   # weak scaling in the sample axis
+    flags = args.flags | (1 if args.fast_sincos else 0)
+    pulses_h = wl["pulses"].to(rdt).pin_memory()
+    target_h = wl["U_target"].pin_memory()
+    pulses_d = pulses_h.to(dev)
+    target_d = target_h.to(dev)
+    tc = uq.target_coeffs(target_d, rdt)
+    err_d = None
+    if wl["explicit"]:
+        # this rank's shard of the (2, B*M_total) error tensor, generated once on the device
+        err_d = uq.philox_errors(B, M, wl["sigma"], seed=1234, offset=0, j0=rank * M, device=dev, dtype=rdt)
+    buf = torch.empty(B + B * L * 2, dtype=rdt, device=dev)
+    Fsum, G = buf[:B], buf[B:]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def step_device(i):
+        ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags)
+        if group is not None:
+            dist.all_reduce(buf, group=group)
+        return ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
+
+    def barrier():
+        if group is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+
+    # ---- timed region: K steps, each bracketed by events; L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        kev[i][0].record()
+        ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags)
+        kev[i][1].record()
+        if group is not None:
+            dist.all_reduce(buf, group=group)
+        loss_out = ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
+        ev[i][1].record()
+    barrier()
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    loss_val = float(loss_out[0].item())
+
+    # ---- end-to-end: public API, host buffers, H2D + D2H inside the timed region
+    grad_h = torch.empty(B, L, 2, dtype=rdt).pin_memory()
+    loss_h = torch.empty(1, dtype=rdt).pin_memory()
+    err_h = err_d.cpu().pin_memory() if err_d is not None else None
+
+    def step_e2e(i):
+        p = pulses_h.to(dev, non_blocking=True).requires_grad_(True)
+        T = target_h.to(dev, non_blocking=True)
+        if err_h is None:
+            val, _ = uq.fused_propagate_loss(p, T, monte_carlo=M_total, sigma=wl["sigma"], seed=1234, offset=i,
+                                             loss="sharp", flags=flags, group=group)
+        elif world == 1:
+            val, _ = uq.fused_propagate_loss(p, T, error=err_h.to(dev, non_blocking=True), monte_carlo=M_total,
+                                             loss="sharp", flags=flags)
+        else:   # explicit eps at N>1: every rank copies in only its own shard of the (2, B*M_total) tensor
+            val, _ = _sharded_explicit(uq, ops, p, T, err_h.to(dev, non_blocking=True), M, M_total, rank, group, flags)
+        val.backward()
+        grad_h.copy_(p.grad, non_blocking=True)
+        loss_h.copy_(val.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = max(e2e_ms, e2e_wall_ms)         # host-side work counts end to end
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- max over ranks
+    t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    step_ms, kern_ms, e2e_ms = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        props_step = float(B) * M_total * L
+        value = props_step / (step_ms * 1e-3)
+        props_kernel = float(B) * M * L                       # one launch, one GPU
+        ach_tflops = props_kernel * FLOP_PER_PROP_FWDBWD / (kern_ms * 1e-3) / 1e12
+        peak_mode = 1 if rdt == torch.float64 else 0
+        try:
+            peak_meas, _ = uq.fp32_peak_tflops(4096, peak_mode)
+            peak2, _ = uq.fp32_peak_tflops(4096, 2) if peak_mode == 0 else (None, None)
+        except Exception:
+            peak_meas, peak2 = None, None
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+        nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12 * (0.5 if rdt == torch.float64 else 1.0)
+        peak = nominal
+        h2d = pulses_h.numel() * pulses_h.element_size() + target_h.numel() * target_h.element_size()
+        if err_h is not None:
+            h2d += err_h.numel() * err_h.element_size()
+        d2h = grad_h.numel() * grad_h.element_size() + loss_h.element_size()
+        line = {
+            "metric": "SU(2) propagations/s fwd+bwd", "value": value, "unit": "prop/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": ("BASELINE config 5 slice (curriculum, Philox eps on-chip)" if args.workload == "curriculum"
+                                    else "BASELINE config 3 (GRAPE, explicit eps)"),
+                       "targets_B": B, "pulses_L": L, "samples_per_target_per_gpu": M, "samples_per_target_total": M_total,
+                       "props_per_step": props_step, "loss": "sharp", "sincos": "mufu" if args.fast_sincos else "poly",
+                       "sharding": f"samples x{world}", "l2_flush_between_steps": True,
+                       "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "e2e": {"value": props_step / (e2e_ms * 1e-3), "unit": "prop/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": args.steps * (2 + (1 if ops._lib.lib().uqoc_su2_workspace_bytes(B, L, M, 0, flags) > 0 else 0)),
+            "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s", "frac": ach_tflops / peak,
+                         "traffic": None, "kernel": "su2_kernel (fused fwd+bwd)", "kernel_ms": kern_ms,
+                         "flop_per_prop": FLOP_PER_PROP_FWDBWD,
+                         "peak_source": f"nominal FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure)",
+                         "measured_ffma_tflops": peak_meas, "measured_ffma2_tflops": peak2},
+            "clocks": clocks, "loss": loss_val,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, L)
+        print(json.dumps(line))
+    if group is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _sharded_explicit(uq, ops, p, T, e_local, M, M_total, rank, group, flags):
+    """Explicit-eps workload at N>1: each rank already holds its own shard of the error tensor."""
+    import torch.distributed as dist
+    tc = uq.target_coeffs(T, p.dtype)
+    return ops._FusedPropagateLoss.apply(p, tc, e_local, M, rank * M, M_total, (1.0, 0.05), 0, 0, "sharp", 0.99, 100, flags,
+                                         group, None, None)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/*
+ * uqoc.h -- C ABI of libuqoc.so: B200 (sm_100a) kernels for disorder-sampled
+ * unitary propagation + fidelity loss, forward and backward.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * shiminki/universal_quantum_optimal_control (paths relative to that repo):
+ *
+ *   SCORE.py   = train/unitary_single_qubit_gate/universal_single_qubit_SCORE.py
+ *   grape.py   = train/GRAPE/grape_train.py
+ *   trainer.py = model/universal_model_trainer.py
+ *   util.py    = visualize/util.py
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller (tensor.data_ptr());
+ *     the library never allocates or frees device memory;
+ *   - arrays are contiguous row-major; "real" is float (dtype = UQOC_F32) or
+ *     double (dtype = UQOC_F64); complex arrays are interleaved (re, im) reals;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises except uqoc_fp32_peak_probe;
+ *   - return value 0 = success, negative = UQOC_E_* (message via
+ *     uqoc_last_error(), thread-local), positive = cudaError_t of a failed launch;
+ *   - re-entrant; no global mutable state; cudaSetDevice is the caller's job;
+ *   - sample layout follows trainer.py:80-82: sample s = b*M + j for target b and
+ *     Monte-Carlo index j; `error` is (E, B*M) with row 0 = delta (ORE), row 1 = eps
+ *     (PLE)  [SCORE.py:113-114].
+ *   - Hamiltonian is the CODE's form (SCORE.py:117-124):
+ *       H = 1/2 (1+eps) (cos(phi) X + sin(phi) Y + delta Z),  U_i = exp(-i H tau_i)
+ */
+#ifndef UQOC_H_
+#define UQOC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UQOC_VERSION 100 /* 0.1.0 */
+
+/* dtype */
+#define UQOC_F32 0
+#define UQOC_F64 1
+
+/* flags (bit mask) */
+#define UQOC_FLAG_FAST_SINCOS 1u /* FP32 only: MUFU sin/cos instead of the polynomial path */
+/* tuning overrides (0 = let the library choose): samples per thread (1,2,4) and lanes per
+ * sample (1,2,4,8,16,32) of the shared-pulse kernels */
+#define UQOC_FLAG_ST(n) (((unsigned)(n) & 0xFu) << 8)
+#define UQOC_FLAG_LPS(n) (((unsigned)(n) & 0x3Fu) << 12)
+#define UQOC_FLAG_SPLITS(n) (((unsigned)(n) & 0xFFFu) << 18)
+
+/* loss kinds for uqoc_loss_finalize (SCORE.py:185-198) */
+#define UQOC_LOSS_SHARP 0      /* log(1+exp(-k(Fbar-tau)))*(1-Fbar)  SCORE.py:193-198 */
+#define UQOC_LOSS_NLL 1        /* -log(Fbar)                          SCORE.py:185-186 */
+#define UQOC_LOSS_INFIDELITY 2 /* 1-Fbar                              SCORE.py:189-190 */
+#define UQOC_LOSS_NONE 3       /* Fbar itself                                          */
+
+/* error codes */
+#define UQOC_E_BADARG (-1)
+#define UQOC_E_UNSUPPORTED (-2)
+#define UQOC_E_WORKSPACE (-3)
+#define UQOC_E_NODEVICE (-4)
+
+int uqoc_version(void);
+const char* uqoc_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Target preparation.  Tr(U_out^dagger T) is linear in the quaternion of U_out;
+ * this turns B complex dxd targets (B, d, d, 2 reals) into the coefficient rows
+ * the kernels consume: SU(2): (B, 8) reals = Re c_0..3, Im c_0..3 (SCORE.py:172-178).
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_target_coeffs(const void* U_target, int64_t B, void* target_c, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Workspace (bytes) needed by the fused / forward kernels for the deterministic
+ * two-stage reduction over sample tiles.  Replaces nothing in the reference
+ * (autograd keeps every (Bm,L,2,2) intermediate instead).
+ * ------------------------------------------------------------------------ */
+int64_t uqoc_su2_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags);
+
+/* ------------------------------------------------------------------------
+ * Fused forward+backward for the trainer's Monte-Carlo step
+ *   replaces trainer.py:80-88 + the autograd backward of SCORE.py:77-183
+ *   (repeat_interleave, error H2D, generator, fidelity, sum over samples, dF/dpulses).
+ *
+ *   pulses      (B, L, 2) reals [phi, tau]  -- NOT repeated M times
+ *   target_c    (B, 8) from uqoc_su2_target_coeffs
+ *   err         (2, B*M) explicit errors, or NULL => on-chip Philox4x32-10 + Box-Muller
+ *                with delta ~ N(0, sig_d^2), eps ~ N(0, sig_e^2)  (replaces SCORE.py:158-161
+ *                + the H2D copy at trainer.py:82); counter = (j0+j, b, offset), key = seed
+ *   weight      NULL, or (B*M) per-sample cotangent dLoss/dF_s (general autograd backward)
+ *   M           samples per target processed by THIS call (this rank's shard)
+ *   j0          global index of this call's first sample (Philox counter base)
+ *   F_out       NULL or (B*M): per-sample fidelity  (SCORE.py:168-183)
+ *   err_out     NULL or (2, B*M): the errors actually used
+ *   Fsum        (B): sum_j F[b,j]
+ *   G           (B, L, 2): sum_j weight * dF[b,j]/d pulses[b]   (unscaled by the loss)
+ *   workspace   >= uqoc_su2_workspace_bytes(...) bytes
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, const void* weight,
+                    int64_t B, int64_t L, int64_t M, int64_t j0,
+                    double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                    void* F_out, void* err_out, void* Fsum, void* G,
+                    void* workspace, int64_t workspace_bytes,
+                    int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Forward only with pulses shared per target (trainer.py:113-120 evaluate;
+ * util.py:214-223 / 244-249 sweeps where one sequence is expand()ed).
+ *   U_out  NULL or (B*M, 2, 2, 2): composite unitary U_L...U_1 (SCORE.py:145)
+ *   F_out  NULL or (B*M);  Fsum NULL or (B);  err_out NULL or (2,B*M)
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_forward(const void* pulses, const void* target_c, const void* err,
+                     int64_t B, int64_t L, int64_t M, int64_t j0,
+                     double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                     void* U_out, void* F_out, void* err_out, void* Fsum,
+                     void* workspace, int64_t workspace_bytes,
+                     int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Strict reference signature: one pulse row PER SAMPLE.
+ *   replaces batched_unitary_generator (SCORE.py:77-145, grape.py:78-138)
+ *   pulses (Bm, L, 2), err (2, Bm)  ->  U_out (Bm, 2, 2) complex
+ * and its autograd backward (LinalgMatrixExpBackward0 + BmmBackward0 chain):
+ *   grad_U (Bm, 2, 2) complex cotangent (torch convention dL = Re sum conj(g) dU)
+ *   -> grad_pulses (Bm, L, 2)
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_generator_forward(const void* pulses, const void* err, int64_t Bm, int64_t L,
+                               void* U_out, int dtype, unsigned flags, void* stream);
+int uqoc_su2_generator_backward(const void* pulses, const void* err, const void* grad_U,
+                                int64_t Bm, int64_t L, void* grad_pulses,
+                                int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Loss epilogue (SCORE.py:185-198 applied to the pooled mean, and the chain rule
+ * of loss.backward() at trainer.py:90):
+ *   Fbar = sum_b Fsum[b] / n_total;  loss_out[0] = loss(Fbar); loss_out[1] = Fbar;
+ *   loss_out[2] = dloss/dFbar;  G[...] *= dloss/dFbar / n_total   (in place, if G != NULL)
+ * n_total = B * M_global (all ranks), so after an all-reduce of [Fsum | G] every
+ * rank gets identical loss and gradients.
+ * ------------------------------------------------------------------------ */
+int uqoc_loss_finalize(const void* Fsum, int64_t B, double n_total, int loss_kind,
+                       double tau, double k, void* G, int64_t G_numel, void* loss_out,
+                       int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Stand-alone fidelity on materialised unitaries, for callers that keep the reference's
+ * three-call structure (generator -> fidelity_fn -> loss_fn, trainer.py:84-88):
+ *   F[s] = (|Tr(U_out[s]^dagger U_target[s])|^2 + d) / (d (d+1))         SCORE.py:168-183
+ *   U_out (Bm, d, d) complex; U_target complex with `target_stride` reals between
+ *   consecutive samples (0 = one target broadcast to all samples, 2*d*d = per-sample)
+ * backward: grad_U = grad_F * 2/(d(d+1)) * conj(tr) * U_target  (torch complex convention).
+ * uqoc_sum: deterministic sum of n reals into out[0] (the mean of SCORE.py:186/190/194 is
+ * sum / n); workspace >= 1024 reals when n > 4096.
+ * ------------------------------------------------------------------------ */
+int uqoc_fidelity_forward(const void* U_out, const void* U_target, int64_t Bm, int d, int64_t target_stride,
+                          void* F, int dtype, void* stream);
+int uqoc_fidelity_backward(const void* U_out, const void* U_target, const void* grad_F, int64_t Bm, int d,
+                           int64_t target_stride, void* grad_U, int dtype, void* stream);
+int uqoc_sum(const void* x, int64_t n, void* out, void* workspace, int64_t workspace_bytes, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Device-side error sampler: replaces get_ore_ple_error_distribution
+ * (SCORE.py:158-161) -- err_out (2, B*M), same Philox stream as the fused kernels.
+ * ------------------------------------------------------------------------ */
+int uqoc_philox_errors(int64_t B, int64_t M, int64_t j0, double sig_d, double sig_e,
+                       uint64_t seed, uint64_t offset, void* err_out, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Roofline denominator: dependency-free FFMA loop on every SM, timed with CUDA
+ * events inside the call (synchronises).  Returns achieved TFLOP/s in *tflops:
+ * dtype UQOC_F32 = scalar FFMA, UQOC_F64 = DFMA, 2 = packed FFMA2 (f32x2).
+ * ------------------------------------------------------------------------ */
+int uqoc_fp32_peak_probe(int iters, int dtype, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UQOC_H_ */

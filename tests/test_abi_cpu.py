@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/uqoc.h declares, argument validation happens before any device work, and CPU tensors
+are rejected (no fallback).  No compute calls: runs without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import universal_quantum_optimal_control_b200 as uq
+from universal_quantum_optimal_control_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", fn)).read()
+            names |= set(re.findall(r"\b(uqoc_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported by libuqoc.so"
+    # and the ctypes table covers the header one to one
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_version_and_error_string():
+    lib = _lib.lib()
+    assert lib.uqoc_version() == 100
+    # bad argument -> negative code + message, no device touched
+    rc = lib.uqoc_su2_fwdbwd(None, None, None, None, 1, 1, 1, 0, 1.0, 0.05, 0, 0, None, None, None, None, None, 0, 7, 0, None)
+    assert rc == -1
+    assert b"dtype" in lib.uqoc_last_error()
+    rc = lib.uqoc_su2_forward(None, None, None, 0, 4, 4, 0, 1.0, 0.05, 0, 0, None, None, None, None, None, 0, 0, 0, None)
+    assert rc == -1 and b"B out of range" in lib.uqoc_last_error()
+
+
+def test_workspace_query_is_pure():
+    lib = _lib.lib()
+    # B=1 with many samples splits across blocks -> needs workspace; many targets do not
+    assert lib.uqoc_su2_workspace_bytes(1, 256, 65536, 0, 0) > 0
+    assert lib.uqoc_su2_workspace_bytes(4096, 256, 4096, 0, 0) == 0
+    assert lib.uqoc_su2_workspace_bytes(0, 256, 16, 0, 0) == 0
+
+
+def test_shape_validation_matches_reference():
+    # SCORE.py:99-100: ValueError("'pulses' must have shape (B, L, 2)")
+    with pytest.raises(ValueError, match=r"'pulses' must have shape \(B, L, 2\)"):
+        uq.batched_unitary_generator(torch.zeros(3, 4, 3), torch.zeros(2, 3))
+    with pytest.raises(ValueError, match=r"'pulses' must have shape \(B, L, 2\)"):
+        uq.batched_unitary_generator(torch.zeros(3, 4), torch.zeros(2, 3))
+    with pytest.raises(ValueError):
+        uq.fused_propagate_loss(torch.zeros(3, 4, 5), torch.zeros(3, 2, 2), monte_carlo=4)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        uq.batched_unitary_generator(torch.zeros(3, 4, 2), torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        uq.fused_propagate_loss(torch.zeros(3, 4, 2), torch.zeros(3, 2, 2, dtype=torch.complex64), monte_carlo=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        uq.fidelity(torch.zeros(3, 2, 2, dtype=torch.complex64), torch.zeros(3, 2, 2, dtype=torch.complex64), 1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "universal_quantum_optimal_control_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "/root/reference" not in src, f
+
+
+def test_tuning_flags_packing():
+    f = uq.tuning_flags(st=4, lps=1, splits=7, fast_sincos=True)
+    assert f & 1 and (f >> 8) & 0xF == 4 and (f >> 12) & 0x3F == 1 and (f >> 18) & 0xFFF == 7

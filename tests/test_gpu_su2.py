@@ -1,0 +1,359 @@
+"""GPU parity tests of the SU(2) path: CUDA kernels (through the C ABI) vs the CPU oracle on
+the same seeded inputs, vs the committed golden vectors of the unmodified reference, and
+size-independent properties at BASELINE-scale shapes.
+
+Tolerances are BASELINE.json's: FP64 mode 1e-12 on fidelity; FP32 mode 1e-5 absolute on
+fidelity and 1e-4 relative (to max |grad|) on gradients, both judged against the FP64
+reference (the reference's own FP32 path is noisier than that)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import universal_quantum_optimal_control_b200 as uq
+from oracle import uqoc_oracle as orc
+from oracle import torch_port as tp
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+F64_TOL_F = 1e-12
+F32_TOL_F = 1e-5
+F32_TOL_G = 1e-4
+
+
+def _t(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _fused(pulses, U_target, error, M, dtype, loss="sharp", flags=0, fast=False, want_F=True):
+    p = _t(pulses, dtype).requires_grad_(True)
+    T = _t(U_target)
+    e = _t(error, dtype)
+    F_out = torch.empty(p.shape[0] * M, dtype=dtype, device=DEV) if want_F else None
+    val, mean_fid = uq.fused_propagate_loss(p, T, error=e, monte_carlo=M, loss=loss, flags=flags, fast_sincos=fast,
+                                            F_out=F_out)
+    val.backward()
+    return (val.item(), p.grad.detach().cpu().numpy().astype(np.float64),
+            None if F_out is None else F_out.cpu().numpy().astype(np.float64), mean_fid.cpu().numpy().astype(np.float64))
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ----------------------------------------------------------------------------- golden: config 1
+@pytest.mark.parametrize("tag", ["sd04", "sd07", "sd10"])
+@pytest.mark.parametrize("loss", ["sharp", "nll", "infidelity"])
+def test_c1_fp64_matches_reference(tag, loss):
+    g = load_golden("c1_train_step.npz")
+    M = int(g["M"])
+    val, grad, F, mf = _fused(g["pulses"], g["U_target"], g[f"error_{tag}"], M, torch.float64, loss)
+    assert np.abs(F - g[f"F64_{tag}"]).max() < F64_TOL_F
+    assert abs(val - g[f"loss64_{loss}_{tag}"]) < 1e-12 * max(1.0, abs(g[f"loss64_{loss}_{tag}"]))
+    assert _relerr(grad, g[f"grad64_{loss}_{tag}"]) < 1e-11
+    assert np.abs(mf - g[f"F64_{tag}"].reshape(4, M).mean(1)).max() < 1e-13
+
+
+@pytest.mark.parametrize("tag", ["sd04", "sd07", "sd10"])
+def test_c1_fp32_within_tolerance_of_fp64_reference(tag):
+    g = load_golden("c1_train_step.npz")
+    M = int(g["M"])
+    val, grad, F, _ = _fused(g["pulses"], g["U_target"], g[f"error_{tag}"], M, torch.float32)
+    assert np.abs(F - g[f"F64_{tag}"]).max() < F32_TOL_F
+    assert _relerr(grad, g[f"grad64_sharp_{tag}"]) < F32_TOL_G
+    assert abs(val - g[f"loss64_sharp_{tag}"]) < 1e-4 * abs(g[f"loss64_sharp_{tag}"])
+    # and at least as close to the truth as the reference's own FP32 path
+    assert np.abs(F - g[f"F64_{tag}"]).max() <= max(np.abs(g[f"F32_{tag}"] - g[f"F64_{tag}"]).max(), 2e-6)
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 7, 33])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_ragged_lengths(L, dtype):
+    g = load_golden("ragged_lengths.npz")
+    M = int(g["M"])
+    val, grad, F, _ = _fused(g[f"L{L}_pulses"], g[f"L{L}_U_target"], g[f"L{L}_error"], M, dtype)
+    tolF, tolG = (F64_TOL_F, 1e-11) if dtype == torch.float64 else (F32_TOL_F, F32_TOL_G)
+    assert np.abs(F - g[f"L{L}_F64"]).max() < tolF
+    assert _relerr(grad, g[f"L{L}_grad64"]) < tolG
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_general_complex_target(dtype):
+    g = load_golden("general_target.npz")
+    val, grad, F, _ = _fused(g["pulses"], g["U_target"], g["error"], int(g["M"]), dtype)
+    tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (2e-5, F32_TOL_G)   # |tr| up to ~3 here
+    assert np.abs(F - g["F64"]).max() < tolF
+    assert _relerr(grad, g["grad64"]) < tolG
+
+
+@pytest.mark.parametrize("dtype,fast", [(torch.float64, False), (torch.float32, False)])
+def test_grape_L256(dtype, fast):
+    g = load_golden("grape_L256.npz")
+    val, grad, F, _ = _fused(g["pulses"], g["U_target"], g["error"], int(g["M"]), dtype, fast=fast)
+    tolF, tolG = (F64_TOL_F, 1e-10) if dtype == torch.float64 else (F32_TOL_F, F32_TOL_G)
+    assert np.abs(F - g["F64"]).max() < tolF
+    assert _relerr(grad, g["grad64"]) < tolG
+
+
+# ----------------------------------------------------------------------------- all launch shapes
+SHAPES = [(1, 1), (2, 1), (4, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)]
+
+
+@pytest.mark.parametrize("st,lps", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_every_launch_shape_matches_oracle(st, lps, dtype):
+    rng = np.random.default_rng(10 * st + lps)
+    B, L, M = 3, 37, 150          # L not a multiple of anything, M not a multiple of the tile
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
+    T = rng.normal(size=(B, 2, 2)) + 1j * rng.normal(size=(B, 2, 2))
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)])
+    if dtype == torch.float32:
+        pulses, err = pulses.astype(np.float32), err.astype(np.float32)
+    want_l, want_g, want_F = orc.loss_and_grad(pulses, T, err, M, "sharp")
+    for splits in (0, 1, 3):
+        flags = uq.tuning_flags(st=st, lps=lps, splits=splits)
+        val, grad, F, _ = _fused(pulses, T, err, M, dtype, flags=flags)
+        tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (3e-5, F32_TOL_G)
+        assert np.abs(F - want_F).max() < tolF, (st, lps, splits)
+        assert _relerr(grad, want_g) < tolG, (st, lps, splits)
+        assert abs(val - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
+
+
+@pytest.mark.parametrize("st,lps", SHAPES)
+def test_forward_only_U_out_every_shape(st, lps):
+    rng = np.random.default_rng(5)
+    B, L, M = 2, 21, 77
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.5, 4.0, (B, L))], -1)   # big angles: sign tracking
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)])
+    T = np.broadcast_to(np.eye(2, dtype=np.complex128), (B, 2, 2)).copy()
+    want_F, want_U = orc.per_sample_fidelity(pulses, T, err, M)
+    from universal_quantum_optimal_control_b200 import ops
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        p = _t(pulses, dtype)
+        U = torch.empty(B * M, 2, 2, 2, dtype=dtype, device=DEV)
+        F = torch.empty(B * M, dtype=dtype, device=DEV)
+        ops._launch_forward(p, uq.target_coeffs(_t(T), dtype), _t(err, dtype), M, 0, (1.0, 0.05), 0, 0, U, F, None, None,
+                            uq.tuning_flags(st=st, lps=lps))
+        Uc = torch.view_as_complex(U).cpu().numpy()
+        assert np.abs(Uc - want_U).max() < tol
+        assert np.abs(F.cpu().numpy() - want_F).max() < 5 * tol
+
+
+# ----------------------------------------------------------------------------- reference-signature adapters
+def test_generator_adapter_matches_golden_and_grid_layout():
+    g = load_golden("grid_sweep.npz")
+    N = g["errors"].shape[1]
+    for dtype, tolU, tolF in ((torch.float64, 1e-12, 1e-12), (torch.float32, 2e-6, F32_TOL_F)):
+        pulse = _t(g["pulse"], dtype)
+        errors = _t(g["errors"], dtype)
+        U = uq.batched_unitary_generator(pulse.expand(N, -1, -1), errors)            # util.py:245 stride-0 view
+        assert U.dtype == (torch.complex128 if dtype == torch.float64 else torch.complex64)
+        assert np.abs(U.cpu().numpy() - g["U64"]).max() < tolU
+        F = uq.fidelity(U, _t(g["U_target"]).expand(N, -1, -1), 1)
+        assert np.abs(F.cpu().numpy() - g["F64"]).max() < tolF
+        # materialised rows take the per-sample kernel: same answer
+        U2 = uq.batched_unitary_generator(pulse.expand(N, -1, -1).contiguous(), errors)
+        assert np.abs(U2.cpu().numpy() - g["U64"]).max() < tolU
+
+
+@pytest.mark.parametrize("key", ["n03", "n04", "n06", "n08", "n09", "n12"])
+def test_score_composite_pulses(key):
+    g = load_golden("score_pulses.npz")
+    K = g["probe"].shape[1]
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 6e-5)):   # L ~ 400, angles up to ~12 rad: ref FP32 noise is 2e-5
+        pulse = _t(g[f"{key}_pulse"], dtype)
+        U = uq.batched_unitary_generator(pulse.expand(K, -1, -1), _t(g["probe"], dtype))
+        F = uq.fidelity(U, _t(g[f"{key}_U_target"]).expand(K, -1, -1), 1).cpu().numpy()
+        assert np.abs(F - g[f"{key}_F64"]).max() < tol
+        assert F[0] > 1 - 1e-4 and F[1] > 0.998 and F[2] > 0.995
+
+
+@pytest.mark.parametrize("loss_name", ["sharp", "nll", "infidelity"])
+def test_reference_three_call_structure_with_autograd(loss_name):
+    """trainer.py:80-90 verbatim with the adapters swapped in: repeat_interleave, generator,
+    loss_fn(U_out, targets, fidelity_fn, nq), backward."""
+    g = load_golden("c1_train_step.npz")
+    M = int(g["M"])
+    loss_fn = {"sharp": uq.sharp_loss, "nll": uq.negative_log_loss, "infidelity": uq.infidelity_loss}[loss_name]
+    for dtype, tolL, tolG in ((torch.float64, 1e-12, 1e-11), (torch.float32, 1e-4, F32_TOL_G)):
+        pulses = _t(g["pulses"], dtype).requires_grad_(True)
+        U_target = _t(g["U_target"]).to(torch.complex128 if dtype == torch.float64 else torch.complex64)
+        error = _t(g["error_sd07"], dtype)
+        pulses_mc = pulses.repeat_interleave(M, dim=0)
+        targets_mc = U_target.repeat_interleave(M, dim=0)
+        U_out = uq.batched_unitary_generator(pulses_mc, error)
+        loss = loss_fn(U_out, targets_mc, uq.fidelity, 1)
+        loss.backward()
+        ref_l, ref_g = g[f"loss64_{loss_name}_sd07"], g[f"grad64_{loss_name}_sd07"]
+        assert abs(loss.item() - ref_l) < tolL * max(1, abs(ref_l))
+        assert _relerr(pulses.grad.cpu().numpy().astype(np.float64), ref_g) < tolG
+
+
+def test_custom_loss_scalar():
+    x = torch.tensor(0.97, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = uq.custom_loss(x)
+    y.backward()
+    assert abs(y.item() - orc.custom_loss(0.97)) < 1e-14
+    assert abs(x.grad.item() - orc.custom_loss_grad(0.97)) < 1e-12
+
+
+def test_propagate_fidelity_arbitrary_downstream_loss():
+    rng = np.random.default_rng(3)
+    B, L, M = 3, 20, 40
+    pulses = np.stack([rng.uniform(-3, 3, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)])
+    _, T = None, orc.batched_unitary_generator(pulses[:, :4], np.zeros((2, B)))
+    wts = rng.uniform(0.5, 1.5, B * M)
+    p = _t(pulses).requires_grad_(True)
+    F = uq.propagate_fidelity(p, _t(T), _t(err), M)
+    ((F ** 2) * _t(wts)).sum().backward()
+    pt = torch.from_numpy(pulses).requires_grad_(True)
+    U = tp.generator_tree(pt.repeat_interleave(M, 0), torch.from_numpy(err))
+    Fr = tp.fidelity(U, torch.from_numpy(T).repeat_interleave(M, 0), 1)
+    ((Fr ** 2) * torch.from_numpy(wts)).sum().backward()
+    assert np.abs(F.detach().cpu().numpy() - Fr.detach().numpy()).max() < 1e-12
+    assert _relerr(p.grad.cpu().numpy(), pt.grad.numpy()) < 1e-11
+
+
+# ----------------------------------------------------------------------------- Philox on-chip errors
+def test_philox_matches_oracle_stream():
+    B, M = 3, 1000
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        e = uq.philox_errors(B, M, (0.7, 0.05), seed=0x1234567890ABCDEF, offset=5, j0=17, dtype=dtype).cpu().numpy()
+        want = orc.philox_errors(B, M, 0.7, 0.05, 0x1234567890ABCDEF, 5, j0=17)
+        assert np.abs(e - want).max() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fused_philox_equals_explicit_errors_and_is_shard_invariant(dtype):
+    rng = np.random.default_rng(11)
+    B, L, M = 5, 24, 600
+    pulses = np.stack([rng.uniform(-3, 3, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
+    T = orc.batched_unitary_generator(pulses[:, :3], np.zeros((2, B)))
+    p = _t(pulses, dtype).requires_grad_(True)
+    err_out = torch.empty(2, B * M, dtype=dtype, device=DEV)
+    F1 = torch.empty(B * M, dtype=dtype, device=DEV)
+    val, mf = uq.fused_propagate_loss(p, _t(T), monte_carlo=M, sigma=(0.7, 0.05), seed=99, offset=2, err_out=err_out, F_out=F1)
+    val.backward()
+    g1 = p.grad.clone()
+    # the errors the kernel reports are the oracle's Philox stream ...
+    want = orc.philox_errors(B, M, 0.7, 0.05, 99, 2)
+    assert np.abs(err_out.cpu().numpy() - want).max() < (1e-12 if dtype == torch.float64 else 2e-6)
+    # ... and feeding them back explicitly gives the same loss and gradient
+    p.grad = None
+    val2, _ = uq.fused_propagate_loss(p, _t(T), error=err_out, monte_carlo=M)
+    val2.backward()
+    assert abs(val.item() - val2.item()) < 1e-6 * abs(val2.item()) if dtype == torch.float32 else abs(val.item() - val2.item()) < 1e-13
+    assert _relerr(g1.cpu().numpy(), p.grad.cpu().numpy()) < (1e-5 if dtype == torch.float32 else 1e-12)
+    # oracle on the reported errors
+    want_l, want_g, want_F = orc.loss_and_grad(pulses, T, err_out.cpu().numpy().astype(np.float64), M)
+    assert np.abs(F1.cpu().numpy() - want_F).max() < (F64_TOL_F if dtype == torch.float64 else F32_TOL_F)
+    assert _relerr(g1.cpu().numpy().astype(np.float64), want_g) < (1e-10 if dtype == torch.float64 else F32_TOL_G)
+    # sample set does not depend on how j is split (what a rank shard does): two half calls == one full call
+    from universal_quantum_optimal_control_b200 import ops
+    tc = uq.target_coeffs(_t(T), dtype)
+    pd = p.detach()
+    Fs = [torch.empty(B, dtype=dtype, device=DEV) for _ in range(2)]
+    Gs = [torch.empty(B, L, 2, dtype=dtype, device=DEV) for _ in range(2)]
+    for r in range(2):
+        ops._launch_fwdbwd(pd, tc, None, None, M // 2, r * (M // 2), (0.7, 0.05), 99, 2, None, None, Fs[r], Gs[r], 0)
+    assert np.abs((Fs[0] + Fs[1]).cpu().numpy() / M - mf.cpu().numpy()).max() < (1e-13 if dtype == torch.float64 else 1e-6)
+
+
+def test_sampler_adapter_statistics():
+    torch.manual_seed(0)
+    e = uq.get_ore_ple_error_distribution(200000, torch.tensor(0.7), 0.05)        # SCORE.py:316 passes 0-d tensors
+    assert e.shape == (2, 200000) and e.is_cuda and e.dtype == torch.float32
+    assert abs(e[0].mean().item()) < 0.01 and abs(e[0].std().item() - 0.7) < 0.01
+    assert abs(e[1].mean().item()) < 0.001 and abs(e[1].std().item() - 0.05) < 0.001
+    e2 = uq.get_ore_ple_error_distribution(200000, 0.7, 0.05)
+    assert not torch.equal(e, e2)                                                   # fresh draw per call
+    d = uq.get_ore_error_distribution(1000, 0.3)
+    assert d.shape == (1000,)
+
+
+# ----------------------------------------------------------------------------- properties at BASELINE sizes
+def test_config3_sized_properties():
+    """GRAPE config (B=1, L=256, M=65536): oracle-free invariants + a sampled oracle check."""
+    torch.manual_seed(42)
+    B, L, M = 1, 256, 65536
+    phi = (torch.rand(B, L, device=DEV) * 2 - 1) * 3.15
+    tau = 0.035 + 0.035 * torch.rand(B, L, device=DEV)
+    pulses = torch.stack([phi, tau], -1).requires_grad_(True)
+    X = torch.tensor([[0, 1], [1, 0]], dtype=torch.complex64, device=DEV)
+    T = torch.matrix_exp(-1j * X * (math.pi / 4))[None]
+    err = uq.get_ore_ple_error_distribution(B * M, 1.0, 0.05, seed=7, offset=0)
+    F = torch.empty(B * M, device=DEV)
+    val, mf = uq.fused_propagate_loss(pulses, T, error=err, monte_carlo=M, F_out=F)
+    val.backward()
+    g1 = pulses.grad.clone()
+    assert F.min().item() >= 1 / 3 - 1e-6 and F.max().item() <= 1 + 1e-6
+    assert abs(F.double().mean().item() - mf.item()) < 1e-6
+    # determinism: bit-identical on a second run
+    pulses.grad = None
+    val2, _ = uq.fused_propagate_loss(pulses, T, error=err, monte_carlo=M)
+    val2.backward()
+    assert torch.equal(g1, pulses.grad) and val.item() == val2.item()
+    # sampled oracle check (every 64th sample) and FP64 kernel vs FP32 kernel
+    idx = np.arange(0, M, 64)
+    want_F, _ = orc.per_sample_fidelity(pulses.detach().cpu().numpy().astype(np.float64), T.cpu().numpy(),
+                                        err.cpu().numpy()[:, idx].astype(np.float64), len(idx))
+    assert np.abs(F.cpu().numpy()[idx] - want_F).max() < F32_TOL_F
+    p64 = pulses.detach().double().requires_grad_(True)
+    v64, _ = uq.fused_propagate_loss(p64, T, error=err.double(), monte_carlo=M)
+    v64.backward()
+    assert _relerr(g1.cpu().numpy().astype(np.float64), p64.grad.cpu().numpy()) < F32_TOL_G
+    assert abs(val.item() - v64.item()) < 1e-4 * abs(v64.item())
+
+
+def test_config5_slice_properties():
+    """Curriculum config slice (many targets x L=256 x Philox samples): linearity in the sample
+    set (two disjoint sample ranges add up) and unit-norm / range invariants."""
+    torch.manual_seed(0)
+    B, L, M = 256, 256, 2048
+    phi = (torch.rand(B, L, device=DEV) * 2 - 1) * 3.15
+    tau = 0.1 + 0.4 * torch.rand(B, L, device=DEV)
+    pulses = torch.stack([phi, tau], -1)
+    ang = torch.rand(B, device=DEV) * math.pi
+    X = torch.tensor([[0, 1], [1, 0]], dtype=torch.complex64, device=DEV)
+    T = torch.matrix_exp(-1j * X[None] * ang[:, None, None])
+    from universal_quantum_optimal_control_b200 import ops
+    tc = uq.target_coeffs(T, torch.float32)
+    out = {}
+    for name, (m, j0) in {"all": (M, 0), "lo": (M // 2, 0), "hi": (M // 2, M // 2)}.items():
+        Fs = torch.empty(B, device=DEV)
+        G = torch.empty(B, L, 2, device=DEV)
+        ops._launch_fwdbwd(pulses, tc, None, None, m, j0, (1.0, 0.05), 5, 0, None, None, Fs, G, 0)
+        out[name] = (Fs, G)
+    assert torch.allclose(out["lo"][0] + out["hi"][0], out["all"][0], rtol=1e-5)
+    scale = out["all"][1].abs().max()
+    assert (out["lo"][1] + out["hi"][1] - out["all"][1]).abs().max() < 1e-4 * scale
+    mf = out["all"][0] / M
+    assert mf.min() >= 1 / 3 - 1e-6 and mf.max() <= 1 + 1e-6
+
+
+def test_identity_and_known_rotations():
+    # tau = 0 -> U = I for every error; a resonant pi pulse about x with no error is -iX
+    L, N = 9, 64
+    pulses = torch.zeros(1, L, 2, device=DEV, dtype=torch.float64)
+    err = uq.get_ore_ple_error_distribution(N, 1.0, 0.05, dtype=torch.float64, seed=1, offset=1)
+    U = uq.batched_unitary_generator(pulses.expand(N, -1, -1), err)
+    assert (U - torch.eye(2, device=DEV)).abs().max() < 1e-15
+    pulses[0, :, 1] = math.pi / L
+    U = uq.batched_unitary_generator(pulses.expand(N, -1, -1), torch.zeros(2, N, device=DEV, dtype=torch.float64))
+    X = torch.tensor([[0, 1], [1, 0]], dtype=torch.complex128, device=DEV)
+    assert (U - (-1j * X)).abs().max() < 1e-14
+    Uh = U.conj().transpose(-1, -2) @ U
+    assert (Uh - torch.eye(2, device=DEV)).abs().max() < 1e-14
+
+
+def test_fast_sincos_mode_reports_accuracy():
+    """MUFU path: not the default; must still be sane (looser bound) -- measured numbers in DESIGN.md."""
+    g = load_golden("grape_L256.npz")
+    val, grad, F, _ = _fused(g["pulses"], g["U_target"], g["error"], int(g["M"]), torch.float32, fast=True)
+    assert np.abs(F - g["F64"]).max() < 5e-4
+    assert _relerr(grad, g["grad64"]) < 5e-3

@@ -1,0 +1,221 @@
+// Common device helpers for libuqoc (sm_100a): scalar traits, quaternion algebra,
+// sin/cos policies, Philox4x32-10 + Box-Muller, per-sample constants.
+//
+// Quaternion <-> SU(2):  U = q0 I - i (q1 X + q2 Y + q3 Z); matrix product == Hamilton
+// product.  One pulse of SCORE.py:117-127 is q = (cos h, r sin h (cos phi, sin phi, delta))
+// with w = sqrt(1+delta^2), r = 1/w, h = tau * (1+eps) w / 2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/uqoc.h"
+
+namespace uqoc {
+
+// ---------------------------------------------------------------- error handling
+void set_error(const char* fmt, ...);
+
+#define UQOC_CHECK_ARG(cond, ...)      \
+    do {                               \
+        if (!(cond)) {                 \
+            uqoc::set_error(__VA_ARGS__); \
+            return UQOC_E_BADARG;      \
+        }                              \
+    } while (0)
+
+inline int launch_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- sincos policies
+enum SinCosPolicy { SC_POLY = 0, SC_MUFU = 1, SC_LIBM = 2 };
+
+// Accurate FP32 sin/cos of h reduced modulo PI (not 2 PI): returns (s, c) = (-1)^k (sin h,
+// cos h) and k in the low bits of `kbits`.  The common sign is irrelevant to the fidelity and
+// to every gradient (U -> -U), so the fused kernels ignore it; the forward kernel that emits
+// U_out tracks the parity.  13 FMA-pipe instructions, no select / branch.
+__device__ __forceinline__ void sincos_modpi(float h, float& s, float& c, int& kbits) {
+    const float MAGIC = 12582912.0f;  // 1.5 * 2^23: round-to-nearest-integer trick
+    float kf = fmaf(h, 0.318309886183790672f, MAGIC);
+    kbits = __float_as_int(kf);
+    kf -= MAGIC;
+    float r = fmaf(kf, -3.14159274101257324f, h);   // pi_hi = float(pi)
+    r = fmaf(kf, 8.74227765734758577e-08f, r);      // -(pi - pi_hi)
+    const float z = r * r;
+    // sin r = r + r z (S0 + S1 z + S2 z^2 + S3 z^3),  |r| <= pi/2  (near-minimax fit)
+    float ps = fmaf(z, 2.6325158160034334e-06f, -1.9822049944195896e-04f);
+    ps = fmaf(z, ps, 8.3332369104027748e-03f);
+    ps = fmaf(z, ps, -1.6666665673255920e-01f);
+    const float rz = r * z;
+    s = fmaf(rz, ps, r);
+    // cos r = 1 + z (C0 + C1 z + ... + C4 z^4)
+    float pc = fmaf(z, -2.6282461362825416e-07f, 2.4774040866759606e-05f);
+    pc = fmaf(z, pc, -1.3888647081330419e-03f);
+    pc = fmaf(z, pc, 4.1666660457849503e-02f);
+    pc = fmaf(z, pc, -0.5f);
+    c = fmaf(z, pc, 1.0f);
+}
+
+template <typename T, int SC>
+struct SinCos;
+
+template <>
+struct SinCos<float, SC_POLY> {
+    static constexpr bool kTracksParity = true;
+    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits) {
+        sincos_modpi(h, s, c, kbits);
+    }
+};
+template <>
+struct SinCos<float, SC_MUFU> {
+    static constexpr bool kTracksParity = false;
+    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits) {
+        kbits = 0;
+        __sincosf(h, &s, &c);
+    }
+};
+template <>
+struct SinCos<float, SC_LIBM> {
+    static constexpr bool kTracksParity = false;
+    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits) {
+        kbits = 0;
+        sincosf(h, &s, &c);
+    }
+};
+template <int SC>
+struct SinCos<double, SC> {
+    static constexpr bool kTracksParity = false;
+    __device__ __forceinline__ static void eval(double h, double& s, double& c, int& kbits) {
+        kbits = 0;
+        sincos(h, &s, &c);
+    }
+};
+
+// ---------------------------------------------------------------- small math traits
+template <typename T>
+struct Real;
+template <>
+struct Real<float> {
+    __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    __device__ __forceinline__ static float rsqrt_acc(float x) { return 1.0f / sqrtf(x); }
+    __device__ __forceinline__ static float sqrt(float x) { return sqrtf(x); }
+};
+template <>
+struct Real<double> {
+    __device__ __forceinline__ static double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    __device__ __forceinline__ static double rsqrt_acc(double x) { return 1.0 / ::sqrt(x); }
+    __device__ __forceinline__ static double sqrt(double x) { return ::sqrt(x); }
+};
+
+// 4-wide row type for the shared-memory pulse tables (one LDS.128 / two for double)
+template <typename T>
+struct alignas(4 * sizeof(T)) Row4 {
+    T x, y, z, w;
+};
+
+// ---------------------------------------------------------------- quaternions
+template <typename T>
+struct Quat {
+    T a, b, c, d;  // scalar, x, y, z
+};
+
+template <typename T>
+__device__ __forceinline__ Quat<T> qmul(const Quat<T>& p, const Quat<T>& q) {
+    Quat<T> r;
+    r.a = p.a * q.a - p.b * q.b - p.c * q.c - p.d * q.d;
+    r.b = p.a * q.b + p.b * q.a + p.c * q.d - p.d * q.c;
+    r.c = p.a * q.c - p.b * q.d + p.c * q.a + p.d * q.b;
+    r.d = p.a * q.d + p.b * q.c - p.c * q.b + p.d * q.a;
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ Quat<T> qconj(const Quat<T>& p) {
+    return Quat<T>{p.a, -p.b, -p.c, -p.d};
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0;
+        const uint64_t p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// (delta, eps) of sample (b, j): counter = (j lo, j hi, b, offset), key = seed.
+// u_k = (x_k + 0.5) 2^-32, Box-Muller pair scaled by (sig_d, sig_e).  Oracle twin:
+// oracle/uqoc_oracle.py::philox_errors.
+template <typename T>
+__device__ __forceinline__ void philox_delta_eps(uint64_t j, uint32_t b, uint64_t seed, uint32_t offset,
+                                                 T sig_d, T sig_e, T& delta, T& eps);
+
+template <>
+__device__ __forceinline__ void philox_delta_eps<float>(uint64_t j, uint32_t b, uint64_t seed, uint32_t offset,
+                                                        float sig_d, float sig_e, float& delta, float& eps) {
+    const Philox4 x = philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), b, offset, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u0 = fmaf((float)x.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u1 = fmaf((float)x.y, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float rad = sqrtf(-2.0f * logf(u0));
+    float sn, cs;
+    sincospif(2.0f * u1, &sn, &cs);
+    delta = sig_d * rad * cs;
+    eps = sig_e * rad * sn;
+}
+template <>
+__device__ __forceinline__ void philox_delta_eps<double>(uint64_t j, uint32_t b, uint64_t seed, uint32_t offset,
+                                                         double sig_d, double sig_e, double& delta, double& eps) {
+    const Philox4 x = philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), b, offset, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u0 = ((double)x.x + 0.5) * 2.3283064365386963e-10;
+    const double u1 = ((double)x.y + 0.5) * 2.3283064365386963e-10;
+    const double rad = ::sqrt(-2.0 * ::log(u0));
+    double sn, cs;
+    sincospi(2.0 * u1, &sn, &cs);
+    delta = sig_d * rad * cs;
+    eps = sig_e * rad * sn;
+}
+
+// ---------------------------------------------------------------- per-sample constants
+// Computed in double and rounded once, so that FP32 mode carries a single rounding (not a
+// chain of them) into the systematic part of every rotation angle of the sample.
+template <typename T>
+struct SampleConst {
+    T a;      // (1+eps) w / 2  : half-angle per unit tau
+    T a2;     // (1+eps) w      : full rotation angle per unit tau
+    T r;      // 1/w
+    T r2;     // 1/w^2
+    T delta;  // detuning
+    T ae;     // (1+eps)/2 = a*r : d h / d tau projected on the axis
+};
+template <typename T>
+__device__ __forceinline__ SampleConst<T> make_sample_const(T delta, T eps) {
+    const double d = (double)delta, e = (double)eps;
+    const double w = ::sqrt(1.0 + d * d);
+    SampleConst<T> k;
+    k.a = (T)(0.5 * (1.0 + e) * w);
+    k.a2 = (T)((1.0 + e) * w);
+    k.r = (T)(1.0 / w);
+    k.r2 = (T)(1.0 / (w * w));
+    k.delta = delta;
+    k.ae = (T)(0.5 * (1.0 + e));
+    return k;
+}
+
+}  // namespace uqoc

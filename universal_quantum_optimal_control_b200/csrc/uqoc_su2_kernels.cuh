@@ -1,0 +1,477 @@
+// SU(2) disorder-sampled propagation kernels (sm_100a).
+//
+// One thread owns ST error samples x one chunk of the pulse train; LPS lanes share a sample
+// (chunked product + warp-shuffle associative scan) when there are too few samples to fill
+// the machine, LPS = 1 (pure register chain) otherwise.  Pulses of the block's target are
+// staged once in shared memory as (cos phi, sin phi, tau) rows and read as broadcast LDS.128.
+//
+// Forward  (SCORE.py:99-145, :168-183):  P <- q_i (x) P, F = ((cr.P)^2 + (ci.P)^2 + 2)/6.
+// Backward (autograd of the same, trainer.py:90): with W_i = conj(S_i) (x) lambda (x) conj(P_i)
+// (S_i = suffix product, P_i = prefix product, lambda = dF/dP_L) the pulse gradients are
+//     dF/dtau_i = (1+eps)/2 * <W_i, n_i>,   dF/dphi_i = c s' B - s'^2 (delta A - W_z)
+// and W_{i-1} = conj(q_i) W_i q_i is a 3-vector rotation about the pulse axis by -2h, done in
+// the pulse's own (phi-rotated) frame.  W_L comes from the prefix scan alone because
+// conj(S_i) = P_i (x) conj(P_L) for unit quaternions, so no L x B x S tensor is ever stored.
+#pragma once
+#include "uqoc_common.cuh"
+
+namespace uqoc {
+
+constexpr int kThreads = 128;  // 4 warps: one per SM sub-partition
+constexpr int kWarps = kThreads / 32;
+
+template <typename T>
+struct Su2Params {
+    const T* pulses;    // (B, L, 2)
+    const T* target_c;  // (B, 8)
+    const T* err;       // (2, B*M) or nullptr (Philox)
+    const T* weight;    // (B*M) or nullptr
+    int B, L, M;
+    int n_tiles, splits;
+    int C;              // chunk length (padded to the gradient-buffer depth)
+    long long j0;
+    T sig_d, sig_e;
+    unsigned long long seed;
+    unsigned offset;
+    T* U_out;      // (B*M, 2, 2, 2) or nullptr
+    T* F_out;      // (B*M) or nullptr
+    T* err_out;    // (2, B*M) or nullptr
+    T* Fsum_part;  // [splits][B]
+    T* G_part;     // [splits][B][L][2]
+};
+
+// gradient-buffer depth: steps buffered in registers before one cross-lane reduction
+template <int LPS>
+struct GradBuf {
+    static constexpr int NB = (LPS == 1) ? 8 : 1;
+};
+
+// ---- transpose-reduce of N per-lane values over the lanes that differ in bits >= BIT --------
+// While more than one value is left each stage halves the values per lane (a lane keeps the
+// half selected by its bit and receives the partner's partial of that half); afterwards plain
+// butterflies.  `base` returns the first original index of the values the lane ends up owning.
+template <typename T, int N, int BIT>
+struct LaneReduce {
+    __device__ __forceinline__ static void run(T* v, int lane, int& base) {
+        if constexpr (BIT < 32) {
+            if constexpr (N > 1) {
+                constexpr int H = N / 2;
+                const bool hi = (lane & BIT) != 0;
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const T keep = hi ? v[j + H] : v[j];
+                    const T send = hi ? v[j] : v[j + H];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+                }
+                if (hi) base += H;
+                LaneReduce<T, H, BIT * 2>::run(v, lane, base);
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], BIT);
+                LaneReduce<T, 1, BIT * 2>::run(v, lane, base);
+            }
+        }
+    }
+};
+// number of values a lane owns at the end and the lane bits over which the result is replicated
+constexpr int reduce_final_count(int n, int bit) { return bit >= 32 ? n : reduce_final_count(n > 1 ? n / 2 : 1, bit * 2); }
+constexpr int reduce_dup_mask(int n, int bit) {
+    return bit >= 32 ? 0 : ((n > 1 ? 0 : bit) | reduce_dup_mask(n > 1 ? n / 2 : 1, bit * 2));
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_up_t(T v, int d, int width) { return __shfl_up_sync(0xffffffffu, v, d, width); }
+template <typename T>
+__device__ __forceinline__ T shfl_t(T v, int src, int width) { return __shfl_sync(0xffffffffu, v, src, width); }
+
+template <typename T>
+__device__ __forceinline__ Quat<T> qshfl_up(const Quat<T>& q, int d, int width) {
+    return Quat<T>{shfl_up_t(q.a, d, width), shfl_up_t(q.b, d, width), shfl_up_t(q.c, d, width), shfl_up_t(q.d, d, width)};
+}
+template <typename T>
+__device__ __forceinline__ Quat<T> qshfl(const Quat<T>& q, int src, int width) {
+    return Quat<T>{shfl_t(q.a, src, width), shfl_t(q.b, src, width), shfl_t(q.c, src, width), shfl_t(q.d, src, width)};
+}
+
+// shared-memory footprint (bytes) of one block
+template <typename T>
+__host__ __device__ inline size_t su2_smem_bytes(int LPS, int C, bool bwd) {
+    const size_t rows = (size_t)LPS * (C + 1);
+    size_t bytes = rows * sizeof(Row4<T>);                             // forward table
+    if (bwd) bytes += rows * sizeof(Row4<T>);                          // backward table
+    if (bwd) bytes += (size_t)kWarps * LPS * C * 2 * sizeof(T);        // per-warp gradient accumulators
+    bytes += 32 * sizeof(T);                                           // block-reduction scratch
+    return bytes;
+}
+
+template <typename T, int ST, int LPS, int SC, bool BWD>
+__global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
+    using R = Real<T>;
+    using SCP = SinCos<T, SC>;
+    constexpr int NB = GradBuf<LPS>::NB;
+    constexpr int SPB = kThreads / LPS;  // sample slots per block
+    constexpr int TS = SPB * ST;         // samples per tile
+    constexpr int NV = 2 * NB;
+
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int C = p.C;
+    const int rows = LPS * (C + 1);
+    Row4<T>* fwd_tab = reinterpret_cast<Row4<T>*>(smem_raw);
+    Row4<T>* bwd_tab = fwd_tab + (BWD ? rows : 0);
+    T* acc = reinterpret_cast<T*>(bwd_tab + rows);       // [kWarps][LPS*C][2] (BWD only)
+    T* scratch = acc + (BWD ? (size_t)kWarps * LPS * C * 2 : 0);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int k = tid % LPS;      // chunk index inside the sample's lane group
+    const int slot = tid / LPS;   // sample slot inside the block
+    const int split = blockIdx.x % p.splits;
+    const int b = blockIdx.x / p.splits;
+    const int L = p.L;
+
+    // ---- stage the target's pulse train: coalesced loads, trig in double, rounded once ----
+    {
+        const T* pb = p.pulses + (size_t)b * L * 2;
+        for (int i = tid; i < LPS * C; i += kThreads) {
+            const int ic = i < L ? i : L - 1;
+            const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
+            const double phi = (double)pb[2 * ic];
+            const double phim = (double)pb[2 * im];
+            const T tau = i < L ? pb[2 * ic + 1] : (T)0;
+            double sn, cs;
+            ::sincos(phi, &sn, &cs);
+            const int row = i + i / C;
+            fwd_tab[row] = Row4<T>{(T)cs, (T)sn, tau, (T)0};
+            if (BWD) {
+                double sd, cd;
+                ::sincos(i == 0 ? 0.0 : phi - phim, &sd, &cd);
+                bwd_tab[row] = Row4<T>{(T)cd, (T)sd, tau, (T)0};
+            }
+        }
+        if (BWD) {
+            for (int i = tid; i < kWarps * LPS * C * 2; i += kThreads) acc[i] = (T)0;
+        }
+    }
+    __syncthreads();
+
+    // target coefficients: Tr(U^dagger T) = (cr + i ci) . P
+    T cr[4], ci[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        cr[m] = p.target_c[(size_t)b * 8 + m];
+        ci[m] = p.target_c[(size_t)b * 8 + 4 + m];
+    }
+
+    const int rowbase = k * (C + 1);
+    const size_t Bm = (size_t)p.B * p.M;
+    T fsum = (T)0;
+
+    for (int tile = split; tile < p.n_tiles; tile += p.splits) {
+        SampleConst<T> kc[ST];
+        bool valid[ST];
+        size_t sidx[ST];
+#pragma unroll
+        for (int u = 0; u < ST; ++u) {
+            const long long j = (long long)tile * TS + u * SPB + slot;
+            valid[u] = j < p.M;
+            sidx[u] = (size_t)b * p.M + (size_t)(valid[u] ? j : 0);
+            T delta = (T)0, eps = (T)0;
+            if (valid[u]) {
+                if (p.err != nullptr) {
+                    delta = p.err[sidx[u]];
+                    eps = p.err[Bm + sidx[u]];
+                } else {
+                    philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, delta, eps);
+                }
+                if (p.err_out != nullptr && k == 0) {
+                    p.err_out[sidx[u]] = delta;
+                    p.err_out[Bm + sidx[u]] = eps;
+                }
+            }
+            kc[u] = make_sample_const<T>(delta, eps);
+        }
+
+        // ---------------- forward sweep over this lane's chunk ----------------
+        Quat<T> P[ST];
+        int parity[ST];
+#pragma unroll
+        for (int u = 0; u < ST; ++u) {
+            P[u] = Quat<T>{(T)1, (T)0, (T)0, (T)0};
+            parity[u] = 0;
+        }
+#pragma unroll 2
+        for (int jj = 0; jj < C; ++jj) {
+            const Row4<T> row = fwd_tab[rowbase + jj];
+#pragma unroll
+            for (int u = 0; u < ST; ++u) {
+                const T h = row.z * kc[u].a;
+                T s, c;
+                int kb;
+                SCP::eval(h, s, c, kb);
+                if (SCP::kTracksParity && !BWD) parity[u] ^= kb;
+                const T sp = s * kc[u].r;
+                const T q1 = sp * row.x, q2 = sp * row.y, q3 = sp * kc[u].delta;
+                const Quat<T> o = P[u];
+                P[u].a = c * o.a - q1 * o.b - q2 * o.c - q3 * o.d;
+                P[u].b = c * o.b + q1 * o.a + q2 * o.d - q3 * o.c;
+                P[u].c = c * o.c - q1 * o.d + q2 * o.a + q3 * o.b;
+                P[u].d = c * o.d + q1 * o.c - q2 * o.b + q3 * o.a;
+            }
+        }
+
+        // ---------------- associative scan over the LPS lanes of a sample ----------------
+        Quat<T> PL[ST];
+#pragma unroll
+        for (int u = 0; u < ST; ++u) {
+            if constexpr (LPS > 1) {
+#pragma unroll
+                for (int d = 1; d < LPS; d <<= 1) {
+                    const Quat<T> o = qshfl_up(P[u], d, LPS);
+                    const Quat<T> n = qmul(P[u], o);   // later pulses on the left
+                    if (k >= d) P[u] = n;
+                }
+                PL[u] = qshfl(P[u], LPS - 1, LPS);
+                if (SCP::kTracksParity && !BWD) {
+#pragma unroll
+                    for (int d = 1; d < LPS; d <<= 1) parity[u] ^= __shfl_xor_sync(0xffffffffu, parity[u], d);
+                }
+            } else {
+                PL[u] = P[u];
+            }
+            // unit-norm projection: removes the radial part of the accumulated rounding error
+            const T n2 = PL[u].a * PL[u].a + PL[u].b * PL[u].b + PL[u].c * PL[u].c + PL[u].d * PL[u].d;
+            const T inv = R::rsqrt_acc(n2);
+            PL[u].a *= inv; PL[u].b *= inv; PL[u].c *= inv; PL[u].d *= inv;
+        }
+
+        // ---------------- fidelity epilogue ----------------
+        T trr[ST], tri[ST];
+#pragma unroll
+        for (int u = 0; u < ST; ++u) {
+            trr[u] = cr[0] * PL[u].a + cr[1] * PL[u].b + cr[2] * PL[u].c + cr[3] * PL[u].d;
+            tri[u] = ci[0] * PL[u].a + ci[1] * PL[u].b + ci[2] * PL[u].c + ci[3] * PL[u].d;
+            const T F = (trr[u] * trr[u] + tri[u] * tri[u] + (T)2) * (T)(1.0 / 6.0);
+            if (valid[u] && k == 0) {
+                fsum += F;
+                if (p.F_out != nullptr) p.F_out[sidx[u]] = F;
+                if (!BWD && p.U_out != nullptr) {
+                    const T sg = (parity[u] & 1) ? (T)-1 : (T)1;
+                    T* U = p.U_out + sidx[u] * 8;
+                    // U = q0 I - i (q1 X + q2 Y + q3 Z), row-major interleaved (re, im)
+                    U[0] = sg * PL[u].a;  U[1] = -sg * PL[u].d;
+                    U[2] = -sg * PL[u].c; U[3] = -sg * PL[u].b;
+                    U[4] = sg * PL[u].c;  U[5] = -sg * PL[u].b;
+                    U[6] = sg * PL[u].a;  U[7] = sg * PL[u].d;
+                }
+            }
+        }
+
+        if constexpr (BWD) {
+            // ---------------- adjoint seed at the end of this lane's chunk ----------------
+            T A[ST], Bq[ST], W3[ST];
+            {
+                const Row4<T> rowL = fwd_tab[rowbase + C - 1];
+#pragma unroll
+                for (int u = 0; u < ST; ++u) {
+                    T wgt = (T)0;
+                    if (valid[u]) wgt = p.weight != nullptr ? p.weight[sidx[u]] : (T)1;
+                    const T fr = wgt * trr[u] * (T)(1.0 / 3.0), fi = wgt * tri[u] * (T)(1.0 / 3.0);
+                    const Quat<T> lam{fr * cr[0] + fi * ci[0], fr * cr[1] + fi * ci[1],
+                                      fr * cr[2] + fi * ci[2], fr * cr[3] + fi * ci[3]};
+                    Quat<T> Wq;
+                    if constexpr (LPS > 1) {
+                        const Quat<T> Lam = qmul(qconj(PL[u]), lam);
+                        Wq = qmul(qmul(P[u], Lam), qconj(P[u]));
+                    } else {
+                        Wq = qmul(lam, qconj(PL[u]));
+                    }
+                    A[u] = Wq.b * rowL.x + Wq.c * rowL.y;
+                    Bq[u] = Wq.c * rowL.x - Wq.b * rowL.y;
+                    W3[u] = Wq.d;
+                }
+            }
+            // ---------------- backward sweep ----------------
+            for (int jb = C / NB - 1; jb >= 0; --jb) {
+                T v[NV];
+#pragma unroll
+                for (int e = NB - 1; e >= 0; --e) {
+                    const Row4<T> row = bwd_tab[rowbase + jb * NB + e];
+                    T gp = (T)0, gt = (T)0;
+#pragma unroll
+                    for (int u = 0; u < ST; ++u) {
+                        const T h = row.z * kc[u].a;
+                        T s, c;
+                        int kb;
+                        SCP::eval(h, s, c, kb);
+                        const T s2 = s + s;
+                        const T C2 = R::fma(-s2, s, (T)1);        // cos 2h
+                        const T Sr = (s2 * kc[u].r) * c;          // sin 2h / w
+                        const T k1 = R::fma(-C2, kc[u].r2, kc[u].r2);  // (1 - cos 2h)/w^2
+                        const T dl = kc[u].delta;
+                        const T t = R::fma(dl, W3[u], A[u]);      // w <W, n>
+                        const T uu = R::fma(dl, A[u], -W3[u]);
+                        gt = R::fma(kc[u].ae, t, gt);
+                        gp = R::fma(Sr, Bq[u], gp);
+                        gp = R::fma(-k1, uu, gp);
+                        const T K = k1 * t, BS = Bq[u] * Sr;
+                        T A1 = R::fma(A[u], C2, K);
+                        A1 = R::fma(dl, BS, A1);
+                        T B1 = Bq[u] * C2;
+                        B1 = R::fma(-uu, Sr, B1);
+                        T Wz = R::fma(W3[u], C2, -BS);
+                        W3[u] = R::fma(dl, K, Wz);
+                        // into the frame of pulse i-1: rotate by (phi_i - phi_{i-1})
+                        A[u] = R::fma(-B1, row.y, A1 * row.x);
+                        Bq[u] = R::fma(B1, row.x, A1 * row.y);
+                    }
+                    v[2 * e] = gp;
+                    v[2 * e + 1] = gt;
+                }
+                int base = 0;
+                LaneReduce<T, NV, LPS>::run(v, lane, base);
+                constexpr int NF = reduce_final_count(NV, LPS);
+                constexpr int DUP = reduce_dup_mask(NV, LPS);
+                if ((lane & DUP) == 0) {
+                    T* dst = acc + ((size_t)(warp * LPS + k) * C + (size_t)jb * NB) * 2 + base;
+#pragma unroll
+                    for (int m = 0; m < NF; ++m) dst[m] += v[m];
+                }
+            }
+        }
+    }
+
+    // ---------------- block epilogue: deterministic fixed-order reductions ----------------
+    {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+        if (lane == 0) scratch[warp] = fsum;
+    }
+    __syncthreads();
+    if (tid == 0 && p.Fsum_part != nullptr) {
+        T tot = (T)0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tot += scratch[w];
+        p.Fsum_part[(size_t)split * p.B + b] = tot;
+    }
+    if constexpr (BWD) {
+        T* gout = p.G_part + ((size_t)split * p.B + b) * L * 2;
+        const int LC2 = LPS * C * 2;
+        for (int i = tid; i < 2 * L; i += kThreads) {
+            T tot = (T)0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
+            gout[i] = (i & 1) ? tot : tot * (T)0.5;   // d/dphi carries the 1/2 of sin 2h = 2 s c
+        }
+    }
+}
+
+// ---- second stage: fixed-order sum of the per-split partials --------------------------------
+template <typename T>
+__global__ void su2_reduce_partials(const T* __restrict__ Fsum_part, const T* __restrict__ G_part, int splits,
+                                    int B, long long n_g /* B*L*2 or 0 */, T* __restrict__ Fsum, T* __restrict__ G) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_g) {
+        T tot = (T)0;
+        for (int s = 0; s < splits; ++s) tot += G_part[(size_t)s * n_g + i];
+        G[i] = tot;
+    }
+    if (Fsum != nullptr && i < B) {
+        T tot = (T)0;
+        for (int s = 0; s < splits; ++s) tot += Fsum_part[(size_t)s * B + i];
+        Fsum[i] = tot;
+    }
+}
+
+// =============================================================================================
+// Strict reference signature: one pulse row per sample (SCORE.py:77-145) and its backward.
+// One thread per sample; pulse rows are walked through L1 (each 128 B line serves 16 steps).
+// =============================================================================================
+template <typename T, int SC>
+__global__ void __launch_bounds__(128) su2_generator_fwd_kernel(const T* __restrict__ pulses, const T* __restrict__ err,
+                                                                long long Bm, int L, T* __restrict__ U_out) {
+    using SCP = SinCos<T, SC_LIBM>;
+    const long long s_idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_idx >= Bm) return;
+    const SampleConst<T> kc = make_sample_const<T>(err[s_idx], err[Bm + s_idx]);
+    const T* row = pulses + (size_t)s_idx * L * 2;
+    Quat<T> P{(T)1, (T)0, (T)0, (T)0};
+    for (int i = 0; i < L; ++i) {
+        const T phi = row[2 * i], tau = row[2 * i + 1];
+        T sp_, cp_, s, c;
+        int kb;
+        SCP::eval(phi, sp_, cp_, kb);
+        SCP::eval(tau * kc.a, s, c, kb);
+        const T sp = s * kc.r;
+        const Quat<T> q{c, sp * cp_, sp * sp_, sp * kc.delta};
+        P = qmul(q, P);
+    }
+    const T n2 = P.a * P.a + P.b * P.b + P.c * P.c + P.d * P.d;
+    const T inv = Real<T>::rsqrt_acc(n2);
+    P.a *= inv; P.b *= inv; P.c *= inv; P.d *= inv;
+    T* U = U_out + (size_t)s_idx * 8;
+    U[0] = P.a;  U[1] = -P.d;
+    U[2] = -P.c; U[3] = -P.b;
+    U[4] = P.c;  U[5] = -P.b;
+    U[6] = P.a;  U[7] = P.d;
+}
+
+template <typename T, int SC>
+__global__ void __launch_bounds__(128) su2_generator_bwd_kernel(const T* __restrict__ pulses, const T* __restrict__ err,
+                                                                const T* __restrict__ grad_U, long long Bm, int L,
+                                                                T* __restrict__ grad_pulses) {
+    using SCP = SinCos<T, SC_LIBM>;
+    using R = Real<T>;
+    const long long s_idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_idx >= Bm) return;
+    const SampleConst<T> kc = make_sample_const<T>(err[s_idx], err[Bm + s_idx]);
+    const T* row = pulses + (size_t)s_idx * L * 2;
+    T* grow = grad_pulses + (size_t)s_idx * L * 2;
+    Quat<T> P{(T)1, (T)0, (T)0, (T)0};
+    for (int i = 0; i < L; ++i) {
+        const T phi = row[2 * i], tau = row[2 * i + 1];
+        T sp_, cp_, s, c;
+        int kb;
+        SCP::eval(phi, sp_, cp_, kb);
+        SCP::eval(tau * kc.a, s, c, kb);
+        const T sp = s * kc.r;
+        const Quat<T> q{c, sp * cp_, sp * sp_, sp * kc.delta};
+        P = qmul(q, P);
+    }
+    // cotangent on U (torch convention dL = Re sum conj(g) dU) -> cotangent on the quaternion
+    const T* g = grad_U + (size_t)s_idx * 8;
+    const Quat<T> lam{g[0] + g[6], -(g[3] + g[5]), g[4] - g[2], g[7] - g[1]};
+    const Quat<T> Wq = qmul(lam, qconj(P));
+    T W1 = Wq.b, W2 = Wq.c, W3 = Wq.d;
+    for (int i = L - 1; i >= 0; --i) {
+        const T phi = row[2 * i], tau = row[2 * i + 1];
+        T sphi, cphi, s, c;
+        int kb;
+        SCP::eval(phi, sphi, cphi, kb);
+        SCP::eval(tau * kc.a, s, c, kb);
+        const T A = W1 * cphi + W2 * sphi;
+        const T Bq = W2 * cphi - W1 * sphi;
+        const T s2 = s + s;
+        const T C2 = R::fma(-s2, s, (T)1);
+        const T Sr = (s2 * kc.r) * c;
+        const T k1 = R::fma(-C2, kc.r2, kc.r2);
+        const T dl = kc.delta;
+        const T t = R::fma(dl, W3, A);
+        const T uu = R::fma(dl, A, -W3);
+        grow[2 * i] = (T)0.5 * (Sr * Bq - k1 * uu);
+        grow[2 * i + 1] = kc.ae * t;
+        const T K = k1 * t, BS = Bq * Sr;
+        const T A1 = R::fma(dl, BS, R::fma(A, C2, K));
+        const T B1 = R::fma(-uu, Sr, Bq * C2);
+        W3 = R::fma(dl, K, R::fma(W3, C2, -BS));
+        W1 = A1 * cphi - B1 * sphi;
+        W2 = A1 * sphi + B1 * cphi;
+    }
+}
+
+// ---- host-side launch plan shared by all instantiation units ---------------------------------
+struct Su2Plan {
+    int st, lps, splits, n_tiles, C;
+    size_t smem;
+};
+
+}  // namespace uqoc

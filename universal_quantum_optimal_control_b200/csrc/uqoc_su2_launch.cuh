@@ -1,0 +1,51 @@
+// Template dispatch (ST, LPS, BWD) -> kernel launch.  Included by one translation unit per
+// (scalar type, sin/cos policy) so the 16 instantiations of each compile in parallel.
+#pragma once
+#include "uqoc_su2_kernels.cuh"
+
+namespace uqoc {
+
+template <typename T, int SC>
+int su2_launch(const Su2Params<T>& p, const Su2Plan& plan, bool bwd, cudaStream_t stream);
+
+template <typename T, int ST, int LPS, int SC, bool BWD>
+static int su2_launch_one(const Su2Params<T>& p, const Su2Plan& plan, cudaStream_t stream) {
+    auto kern = su2_kernel<T, ST, LPS, SC, BWD>;
+    if (plan.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        if (e != cudaSuccess) {
+            set_error("su2 kernel needs %zu bytes of shared memory (L too large): %s", plan.smem, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return UQOC_E_UNSUPPORTED;
+        }
+    }
+    const unsigned grid = (unsigned)((long long)p.B * plan.splits);
+    kern<<<grid, kThreads, plan.smem, stream>>>(p);
+    return launch_status("su2_kernel");
+}
+
+template <typename T, int SC, bool BWD>
+static int su2_launch_bwd(const Su2Params<T>& p, const Su2Plan& plan, cudaStream_t stream) {
+    const int key = plan.st * 100 + plan.lps;
+    switch (key) {
+        case 101: return su2_launch_one<T, 1, 1, SC, BWD>(p, plan, stream);
+        case 201: return su2_launch_one<T, 2, 1, SC, BWD>(p, plan, stream);
+        case 401: return su2_launch_one<T, 4, 1, SC, BWD>(p, plan, stream);
+        case 102: return su2_launch_one<T, 1, 2, SC, BWD>(p, plan, stream);
+        case 104: return su2_launch_one<T, 1, 4, SC, BWD>(p, plan, stream);
+        case 108: return su2_launch_one<T, 1, 8, SC, BWD>(p, plan, stream);
+        case 116: return su2_launch_one<T, 1, 16, SC, BWD>(p, plan, stream);
+        case 132: return su2_launch_one<T, 1, 32, SC, BWD>(p, plan, stream);
+        default:
+            set_error("unsupported launch shape ST=%d LPS=%d", plan.st, plan.lps);
+            return UQOC_E_UNSUPPORTED;
+    }
+}
+
+#define UQOC_INSTANTIATE_SU2(T, SC)                                                                      \
+    template <>                                                                                          \
+    int su2_launch<T, SC>(const Su2Params<T>& p, const Su2Plan& plan, bool bwd, cudaStream_t stream) {   \
+        return bwd ? su2_launch_bwd<T, SC, true>(p, plan, stream) : su2_launch_bwd<T, SC, false>(p, plan, stream); \
+    }
+
+}  // namespace uqoc

@@ -1,0 +1,421 @@
+"""Host-side mirror of the reference's hot-path interface over libuqoc.so.
+
+Two layers:
+
+* ``fused_propagate_loss`` / ``propagate_fidelity`` -- the fused ops that carry the
+  performance (pulses are NOT repeated per Monte-Carlo sample; errors optionally generated
+  on-chip by Philox); they replace ``trainer.py:80-90`` in one call.
+* reference-signature adapters -- ``batched_unitary_generator``, ``fidelity``,
+  ``sharp_loss``, ``negative_log_loss``, ``infidelity_loss``, ``custom_loss``,
+  ``get_ore_ple_error_distribution``, ``get_ore_error_distribution`` -- same names, argument
+  meaning and error behaviour as
+  ``train/unitary_single_qubit_gate/universal_single_qubit_SCORE.py:77-198`` so they can be
+  passed unchanged to ``UniversalModelTrainer`` (``model/universal_model_trainer.py:27-33``).
+
+Everything runs through the C ABI on CUDA tensors; CPU tensors are rejected (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import F32, F64, FLAG_FAST_SINCOS, LOSS_KINDS, check
+
+__all__ = [
+    "fused_propagate_loss", "propagate_fidelity", "batched_unitary_generator", "fidelity",
+    "sharp_loss", "negative_log_loss", "infidelity_loss", "custom_loss",
+    "get_ore_ple_error_distribution", "get_ore_error_distribution", "philox_errors",
+    "target_coeffs", "tuning_flags", "fp32_peak_tflops",
+]
+
+
+# ----------------------------------------------------------------------------- helpers
+def _dt(t: torch.Tensor) -> int:
+    return F64 if t.dtype == torch.float64 else F32
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the uqoc ops have no CPU fallback")
+
+
+def _real_dtype(t: torch.Tensor) -> torch.dtype:
+    if t.dtype in (torch.float64, torch.complex128):
+        return torch.float64
+    return torch.float32
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:
+    """Grow-only scratch buffer per (device, stream) -- the library never allocates."""
+    if nbytes <= 0:
+        return None
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool = False) -> int:
+    """Pack the launch-shape overrides of include/uqoc.h (0 = library heuristic)."""
+    return (FLAG_FAST_SINCOS if fast_sincos else 0) | ((st & 0xF) << 8) | ((lps & 0x3F) << 12) | ((splits & 0xFFF) << 18)
+
+
+def target_coeffs(U_target: torch.Tensor, real_dtype: torch.dtype) -> torch.Tensor:
+    """(B,2,2) complex targets -> (B,8) trace coefficients (``uqoc_su2_target_coeffs``)."""
+    _require_cuda(U_target, "U_target")
+    if U_target.ndim != 3 or U_target.shape[-2:] != (2, 2):
+        raise ValueError("'U_target' must have shape (B, 2, 2)")
+    if not U_target.is_complex():
+        U_target = U_target.to(torch.complex64 if real_dtype == torch.float32 else torch.complex128)
+    ur = torch.view_as_real(U_target.resolve_conj()).to(real_dtype).contiguous()
+    out = torch.empty(U_target.shape[0], 8, dtype=real_dtype, device=U_target.device)
+    check(_lib.lib().uqoc_su2_target_coeffs(_ptr(ur), U_target.shape[0], _ptr(out), _dt(out), _stream(out.device)),
+          "uqoc_su2_target_coeffs")
+    return out
+
+
+def philox_errors(B: int, M: int, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, offset: int = 0, j0: int = 0,
+                  device="cuda", dtype=torch.float32) -> torch.Tensor:
+    """(2, B*M) errors from the library's counter-based stream (``uqoc_philox_errors``)."""
+    out = torch.empty(2, B * M, dtype=dtype, device=device)
+    check(_lib.lib().uqoc_philox_errors(B, M, j0, float(sigma[0]), float(sigma[1]), seed, offset, _ptr(out), _dt(out),
+                                        _stream(out.device)), "uqoc_philox_errors")
+    return out
+
+
+def fp32_peak_tflops(iters: int = 4096, mode: int = F32) -> Tuple[float, float]:
+    """Measured dependent-free FMA throughput (TFLOP/s, ms): 0 = FFMA, 1 = DFMA, 2 = FFMA2."""
+    tf, ms = C.c_double(0), C.c_double(0)
+    check(_lib.lib().uqoc_fp32_peak_probe(iters, mode, C.byref(tf), C.byref(ms)), "uqoc_fp32_peak_probe")
+    return tf.value, ms.value
+
+
+# ----------------------------------------------------------------------------- fused op
+def _launch_fwdbwd(pulses, tc, error, weight, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags):
+    B, L, _ = pulses.shape
+    lib = _lib.lib()
+    dt = _dt(pulses)
+    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
+    ws = _workspace(ws_bytes, pulses.device)
+    check(lib.uqoc_su2_fwdbwd(_ptr(pulses), _ptr(tc), _ptr(error), _ptr(weight), B, L, M, j0, float(sigma[0]),
+                              float(sigma[1]), seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws),
+                              ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su2_fwdbwd")
+
+
+def _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, U_out, F_out, err_out, Fsum, flags):
+    B, L, _ = pulses.shape
+    lib = _lib.lib()
+    dt = _dt(pulses)
+    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
+    ws = _workspace(ws_bytes, pulses.device)
+    check(lib.uqoc_su2_forward(_ptr(pulses), _ptr(tc), _ptr(error), B, L, M, j0, float(sigma[0]), float(sigma[1]), seed,
+                               offset, _ptr(U_out), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(ws), ws_bytes, dt, flags,
+                               _stream(pulses.device)), "uqoc_su2_forward")
+
+
+def _finalize(Fsum, n_total, loss, tau, k, G):
+    loss_out = torch.empty(3, dtype=Fsum.dtype, device=Fsum.device)
+    check(_lib.lib().uqoc_loss_finalize(_ptr(Fsum), Fsum.numel(), float(n_total), LOSS_KINDS[loss], float(tau), float(k),
+                                        _ptr(G), 0 if G is None else G.numel(), _ptr(loss_out), _dt(Fsum),
+                                        _stream(Fsum.device)), "uqoc_loss_finalize")
+    return loss_out
+
+
+class _FusedPropagateLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pulses, tc, error, M, j0, M_total, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out):
+        B, L, _ = pulses.shape
+        need_grad = ctx.needs_input_grad[0]
+        buf = torch.empty(B + (B * L * 2 if need_grad else 0), dtype=pulses.dtype, device=pulses.device)
+        Fsum, G = buf[:B], (buf[B:] if need_grad else None)
+        if need_grad:
+            _launch_fwdbwd(pulses, tc, error, None, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags)
+        else:
+            _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, None, F_out, err_out, Fsum, flags)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)   # [Fsum | G]: the one exchange step
+        loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
+        mean_fid = Fsum / M_total
+        if need_grad:
+            ctx.save_for_backward(G.view(B, L, 2))
+        ctx.mark_non_differentiable(mean_fid)
+        return loss_out[0], mean_fid
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_mean):
+        (G,) = ctx.saved_tensors
+        return (g_loss * G,) + (None,) * 15
+
+
+def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error: Optional[torch.Tensor] = None,
+                         monte_carlo: int, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, offset: int = 0,
+                         loss: str = "sharp", tau: float = 0.99, k: float = 100, dtype: Optional[torch.dtype] = None,
+                         fast_sincos: bool = False, flags: int = 0, group=None,
+                         F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None):
+    """Disorder-averaged loss of ``trainer.py:80-88`` and (through autograd) its pulse gradient.
+
+    pulses (B, L, 2) real [phi, tau] (un-repeated); U_target (B, 2, 2) complex;
+    error (2, B*monte_carlo) explicit [delta; eps] with sample s = b*M + j, or None for
+    on-chip Philox N(0, sigma) samples keyed by (seed, offset).  With ``group`` (a
+    torch.distributed process group) every rank handles samples
+    j in [rank*M/R, (rank+1)*M/R) of every target and one all-reduce combines [Fsum | G].
+    Returns ``(loss scalar, mean fidelity per target (B,))``.
+    """
+    if pulses.ndim != 3 or pulses.shape[-1] != 2:
+        raise ValueError("'pulses' must have shape (B, L, 2)")
+    _require_cuda(pulses, "pulses")
+    if loss not in LOSS_KINDS:
+        raise ValueError(f"unknown loss {loss!r}; expected one of {sorted(LOSS_KINDS)}")
+    rdt = dtype or _real_dtype(pulses)
+    B, L, _ = pulses.shape
+    M_total = int(monte_carlo)
+    if U_target.shape[0] != B:
+        raise ValueError(f"U_target batch {U_target.shape[0]} != pulses batch {B}")
+    p = pulses.to(rdt).contiguous()
+    tc = target_coeffs(U_target, rdt)
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    per = (M_total + world - 1) // world
+    j0 = min(rank * per, M_total)
+    M = min(per, M_total - j0)
+    if M <= 0:
+        raise ValueError("monte_carlo must be >= world size")
+    if error is not None:
+        _require_cuda(error, "error")
+        if error.shape != (2, B * M_total):
+            raise ValueError(f"'error' must have shape (2, {B * M_total}), got {tuple(error.shape)}")
+        e = error.to(rdt)
+        if world > 1:
+            e = e.view(2, B, M_total)[:, :, j0:j0 + M]
+        error = e.reshape(2, B * M).contiguous()
+    fl = flags | (FLAG_FAST_SINCOS if fast_sincos else 0)
+    return _FusedPropagateLoss.apply(p, tc, error, M, j0, M_total, tuple(float(s) for s in sigma), int(seed), int(offset),
+                                     loss, tau, k, fl, group, F_out, err_out)
+
+
+class _PropagateFidelity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pulses, tc, error, M, sigma, seed, offset, flags):
+        B, L, _ = pulses.shape
+        F = torch.empty(B * M, dtype=pulses.dtype, device=pulses.device)
+        _launch_forward(pulses, tc, error, M, 0, sigma, seed, offset, None, F, None, None, flags)
+        ctx.save_for_backward(pulses, tc, error if error is not None else pulses.new_empty(0))
+        ctx.args = (M, sigma, seed, offset, flags, error is not None)
+        return F
+
+    @staticmethod
+    def backward(ctx, gF):
+        pulses, tc, error = ctx.saved_tensors
+        M, sigma, seed, offset, flags, has_err = ctx.args
+        B, L, _ = pulses.shape
+        Fsum = torch.empty(B, dtype=pulses.dtype, device=pulses.device)
+        G = torch.empty(B, L, 2, dtype=pulses.dtype, device=pulses.device)
+        _launch_fwdbwd(pulses, tc, error if has_err else None, gF.to(pulses.dtype).contiguous(), M, 0, sigma, seed, offset,
+                       None, None, Fsum, G, flags)
+        return (G,) + (None,) * 7
+
+
+def propagate_fidelity(pulses: torch.Tensor, U_target: torch.Tensor, error: Optional[torch.Tensor], monte_carlo: int, *,
+                       sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, offset: int = 0,
+                       dtype: Optional[torch.dtype] = None, fast_sincos: bool = False, flags: int = 0) -> torch.Tensor:
+    """Per-sample fidelity F (B*M,) of un-repeated pulses, differentiable w.r.t. ``pulses`` for an
+    arbitrary downstream loss (the backward kernel takes dLoss/dF_s as per-sample weights)."""
+    if pulses.ndim != 3 or pulses.shape[-1] != 2:
+        raise ValueError("'pulses' must have shape (B, L, 2)")
+    _require_cuda(pulses, "pulses")
+    rdt = dtype or _real_dtype(pulses)
+    B = pulses.shape[0]
+    M = int(monte_carlo)
+    if error is not None:
+        _require_cuda(error, "error")
+        if error.shape != (2, B * M):
+            raise ValueError(f"'error' must have shape (2, {B * M}), got {tuple(error.shape)}")
+        error = error.to(rdt).contiguous()
+    fl = flags | (FLAG_FAST_SINCOS if fast_sincos else 0)
+    return _PropagateFidelity.apply(pulses.to(rdt).contiguous(), target_coeffs(U_target, rdt), error, M,
+                                    tuple(float(s) for s in sigma), int(seed), int(offset), fl)
+
+
+# ----------------------------------------------------------------------------- reference-signature adapters
+class _Generator(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pulses, error):
+        Bm, L, _ = pulses.shape
+        U = torch.empty(Bm, 2, 2, 2, dtype=pulses.dtype, device=pulses.device)
+        check(_lib.lib().uqoc_su2_generator_forward(_ptr(pulses), _ptr(error), Bm, L, _ptr(U), _dt(pulses), 0,
+                                                    _stream(pulses.device)), "uqoc_su2_generator_forward")
+        ctx.save_for_backward(pulses, error)
+        return torch.view_as_complex(U)
+
+    @staticmethod
+    def backward(ctx, gU):
+        pulses, error = ctx.saved_tensors
+        Bm, L, _ = pulses.shape
+        g = torch.view_as_real(gU.resolve_conj()).to(pulses.dtype).contiguous()
+        gp = torch.empty_like(pulses)
+        check(_lib.lib().uqoc_su2_generator_backward(_ptr(pulses), _ptr(error), _ptr(g), Bm, L, _ptr(gp), _dt(pulses), 0,
+                                                     _stream(pulses.device)), "uqoc_su2_generator_backward")
+        return gp, None
+
+
+def batched_unitary_generator(pulses: torch.Tensor, error: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``batched_unitary_generator`` (SCORE.py:77-145 / grape_train.py:78-138).
+
+    pulses (Bm, L, 2) [phi, tau]; error (2, Bm) [delta; eps] -> (Bm, 2, 2) complex64
+    (complex128 for float64 inputs), differentiable w.r.t. ``pulses``.  A stride-0
+    ``expand``-ed pulse sequence (visualize/util.py:245) takes the shared-pulse kernel.
+    """
+    if pulses.ndim != 3 or pulses.shape[-1] != 2:
+        raise ValueError("'pulses' must have shape (B, L, 2)")
+    _require_cuda(pulses, "pulses")
+    _require_cuda(error, "error")
+    Bm, L, _ = pulses.shape
+    if error.ndim != 2 or error.shape[0] != 2 or error.shape[1] != Bm:
+        raise ValueError(f"'error' must have shape (2, {Bm})")
+    rdt = torch.float64 if (pulses.dtype == torch.float64 or error.dtype == torch.float64) else torch.float32
+    err = error.to(rdt).contiguous()
+    grad_needed = pulses.requires_grad and torch.is_grad_enabled()
+    if Bm > 1 and pulses.stride(0) == 0 and not grad_needed:
+        shared = pulses[0:1].to(rdt).contiguous()
+        U = torch.empty(Bm, 2, 2, 2, dtype=rdt, device=pulses.device)
+        eye = torch.eye(2, dtype=torch.complex64 if rdt == torch.float32 else torch.complex128, device=pulses.device)[None]
+        _launch_forward(shared, target_coeffs(eye, rdt), err, Bm, 0, (0.0, 0.0), 0, 0, U, None, None, None, 0)
+        return torch.view_as_complex(U)
+    return _Generator.apply(pulses.to(rdt).contiguous(), err)
+
+
+class _Fidelity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, T, d, t_stride):
+        Bm = U.shape[0]
+        F = torch.empty(Bm, dtype=U.dtype, device=U.device)
+        check(_lib.lib().uqoc_fidelity_forward(_ptr(U), _ptr(T), Bm, d, t_stride, _ptr(F), _dt(U), _stream(U.device)),
+              "uqoc_fidelity_forward")
+        ctx.save_for_backward(U, T)
+        ctx.args = (d, t_stride)
+        return F
+
+    @staticmethod
+    def backward(ctx, gF):
+        U, T = ctx.saved_tensors
+        d, t_stride = ctx.args
+        gU = torch.empty_like(U)
+        check(_lib.lib().uqoc_fidelity_backward(_ptr(U), _ptr(T), _ptr(gF.to(U.dtype).contiguous()), U.shape[0], d, t_stride,
+                                                _ptr(gU), _dt(U), _stream(U.device)), "uqoc_fidelity_backward")
+        return gU, None, None, None
+
+
+def fidelity(U_out: torch.Tensor, U_target: torch.Tensor, num_qubits: int) -> torch.Tensor:
+    """Drop-in for ``fidelity`` (SCORE.py:168-183): (|Tr(U_out^dagger U_target)|^2 + d) / (d(d+1))."""
+    _require_cuda(U_out, "U_out")
+    _require_cuda(U_target, "U_target")
+    d = 2 ** num_qubits
+    if U_out.ndim != 3 or U_out.shape[-2:] != (d, d):
+        raise ValueError(f"'U_out' must have shape (B, {d}, {d})")
+    rdt = _real_dtype(U_out)
+    cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+    Bm = U_out.shape[0]
+    Ur = torch.view_as_real(U_out.to(cdt).resolve_conj().contiguous())
+    if U_target.ndim == 2 or (U_target.ndim == 3 and (U_target.shape[0] == 1 or U_target.stride(0) == 0)):
+        T = U_target.reshape(-1, d, d)[0:1].to(cdt).resolve_conj().contiguous()
+        t_stride = 0
+    else:
+        if U_target.shape[0] != Bm:
+            raise ValueError("U_target batch does not match U_out")
+        T = U_target.to(cdt).resolve_conj().contiguous()
+        t_stride = 2 * d * d
+    return _Fidelity.apply(Ur, torch.view_as_real(T), d, t_stride)
+
+
+class _MeanLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, F, kind, tau, k):
+        n = F.numel()
+        S = torch.empty(1, dtype=F.dtype, device=F.device)
+        ws = _workspace(1024 * 8, F.device)
+        check(_lib.lib().uqoc_sum(_ptr(F), n, _ptr(S), _ptr(ws), ws.numel(), _dt(F), _stream(F.device)), "uqoc_sum")
+        out = _finalize(S, n, kind, tau, k, None)
+        ctx.save_for_backward(out)
+        ctx.shape = F.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        n = 1
+        for s in ctx.shape:
+            n *= s
+        return (g * out[2] / n).expand(ctx.shape), None, None, None
+
+
+def _mean_loss(F: torch.Tensor, kind: str, tau: float = 0.99, k: float = 100) -> torch.Tensor:
+    _require_cuda(F, "fidelity")
+    if F.dtype not in (torch.float32, torch.float64):
+        F = F.float()
+    return _MeanLoss.apply(F.contiguous(), kind, tau, k)
+
+
+def negative_log_loss(U_out, U_target, fidelity_fn, num_qubits):
+    """Drop-in for SCORE.py:185-186: -log(mean F)."""
+    return _mean_loss(fidelity_fn(U_out, U_target, num_qubits), "nll")
+
+
+def infidelity_loss(U_out, U_target, fidelity_fn, num_qubits):
+    """Drop-in for SCORE.py:189-190: 1 - mean F."""
+    return _mean_loss(fidelity_fn(U_out, U_target, num_qubits), "infidelity")
+
+
+def sharp_loss(U_out, U_target, fidelity_fn, num_qubits, tau=0.99, k=100):
+    """Drop-in for SCORE.py:193-195: custom_loss(mean F, tau, k)."""
+    return _mean_loss(fidelity_fn(U_out, U_target, num_qubits), "sharp", tau, k)
+
+
+def custom_loss(x: torch.Tensor, tau=0.99, k=100):
+    """Drop-in for SCORE.py:197-198: log(1+exp(-k(x-tau))) * (1-x) of a scalar fidelity."""
+    if x.numel() != 1:
+        raise ValueError("custom_loss expects the scalar mean fidelity (SCORE.py:194)")
+    return _mean_loss(x.reshape(1), "sharp", tau, k)
+
+
+_SAMPLER_STATE = {"calls": 0}
+
+
+def get_ore_ple_error_distribution(batch_size: int, delta_std=1.0, epsilon_std=0.05, *, device="cuda",
+                                   dtype=torch.float32, seed: Optional[int] = None,
+                                   offset: Optional[int] = None) -> torch.Tensor:
+    """Drop-in for SCORE.py:158-161, generated on the device: (2, batch_size) with row 0 ~
+    N(0, delta_std^2) and row 1 ~ N(0, epsilon_std^2).  The stream is Philox keyed by
+    ``seed`` (default ``torch.initial_seed()``) and a per-call ``offset`` counter, so runs are
+    reproducible under ``torch.manual_seed`` without a host RNG or an H2D copy."""
+    if seed is None:
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if offset is None:
+        offset = _SAMPLER_STATE["calls"]
+        _SAMPLER_STATE["calls"] += 1
+    return philox_errors(1, int(batch_size), (float(delta_std), float(epsilon_std)), seed, offset, 0, device, dtype)
+
+
+def get_ore_error_distribution(batch_size: int, delta_std=1.0, *, device="cuda", dtype=torch.float32,
+                               seed: Optional[int] = None, offset: Optional[int] = None) -> torch.Tensor:
+    """Drop-in for SCORE.py:154-155 (legacy 1-D ORE sampler)."""
+    return get_ore_ple_error_distribution(batch_size, delta_std, 0.0, device=device, dtype=dtype, seed=seed,
+                                          offset=offset)[0]
