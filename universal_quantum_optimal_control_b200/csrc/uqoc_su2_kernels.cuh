@@ -366,19 +366,30 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
 }
 
 // ---- second stage: fixed-order sum of the per-split partials --------------------------------
+// Block = 32 outputs x 8 split-lanes: lane y sums splits y, y+8, ... (coalesced 128 B rows), then a
+// fixed-order combine over y through shared memory.  Fsum rides along as outputs [n_g, n_g + B).
 template <typename T>
-__global__ void su2_reduce_partials(const T* __restrict__ Fsum_part, const T* __restrict__ G_part, int splits,
-                                    int B, long long n_g /* B*L*2 or 0 */, T* __restrict__ Fsum, T* __restrict__ G) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) su2_reduce_partials(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
+                                                           int splits, int B, long long n_g /* B*L*2 or 0 */,
+                                                           T* __restrict__ Fsum, T* __restrict__ G) {
+    __shared__ T red[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + x;
+    const long long n_f = (Fsum != nullptr) ? B : 0;
+    T tot = (T)0;
     if (i < n_g) {
-        T tot = (T)0;
-        for (int s = 0; s < splits; ++s) tot += G_part[(size_t)s * n_g + i];
-        G[i] = tot;
+        for (int s = y; s < splits; s += 8) tot += G_part[(size_t)s * n_g + i];
+    } else if (i < n_g + n_f) {
+        for (int s = y; s < splits; s += 8) tot += Fsum_part[(size_t)s * B + (i - n_g)];
     }
-    if (Fsum != nullptr && i < B) {
-        T tot = (T)0;
-        for (int s = 0; s < splits; ++s) tot += Fsum_part[(size_t)s * B + i];
-        Fsum[i] = tot;
+    red[y][x] = tot;
+    __syncthreads();
+    if (y == 0) {
+        T t = red[0][x];
+#pragma unroll
+        for (int yy = 1; yy < 8; ++yy) t += red[yy][x];
+        if (i < n_g) G[i] = t;
+        else if (i < n_g + n_f) Fsum[i - n_g] = t;
     }
 }
 
