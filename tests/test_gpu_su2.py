@@ -133,6 +133,9 @@ def test_forward_only_U_out_every_shape(st, lps):
     want_F, want_U = orc.per_sample_fidelity(pulses, T, err, M)
     from universal_quantum_optimal_control_b200 import ops
     for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        if dtype == torch.float32:   # judge the FP32 kernel on the inputs it actually receives
+            want_F, want_U = orc.per_sample_fidelity(pulses.astype(np.float32).astype(np.float64), T,
+                                                     err.astype(np.float32).astype(np.float64), M)
         p = _t(pulses, dtype)
         U = torch.empty(B * M, 2, 2, 2, dtype=dtype, device=DEV)
         F = torch.empty(B * M, dtype=dtype, device=DEV)

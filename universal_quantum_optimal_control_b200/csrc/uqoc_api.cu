@@ -290,10 +290,9 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     else rc = su2_launch<T, SC_POLY>(p, plan, bwd, stream);
     if (rc != 0) return rc;
     if (plan.splits > 1 && (Fsum != nullptr || n_g > 0)) {
-        const long long n = n_g > B ? n_g : B;
-        const int threads = 256;
-        const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-        su2_reduce_partials<T><<<blocks, threads, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, (T*)Fsum, (T*)G);
+        const long long n = n_g + (Fsum != nullptr ? B : 0);
+        const unsigned blocks = (unsigned)((n + 31) / 32);
+        su2_reduce_partials<T><<<blocks, 256, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, (T*)Fsum, (T*)G);
         return launch_status("su2_reduce_partials");
     }
     return 0;
