@@ -56,20 +56,22 @@ def main():
             emit(probe="peak", mode=name, tflops=tf, ms=ms)
     if "sweep" in which:
         cases = [("curriculum", 4096, 256, 4096, (0.1, 0.5)), ("grape", 1, 256, 65536, (0.035, 0.07)),
-                 ("c1", 4, 16, 256, (0.1, 0.5)), ("mid", 64, 100, 1000, (0.1, 0.5)), ("shipped", 200, 100, 1000, (0.1, 0.5))]
+                 ("shipped", 200, 100, 1000, (0.1, 0.5))]
+        if "small" in which:
+            cases += [("c1", 4, 16, 256, (0.1, 0.5)), ("mid", 64, 100, 1000, (0.1, 0.5))]
         for name, B, L, M, tau in cases:
             for dtype, dn in ((torch.float32, "f32"), (torch.float64, "f64")):
                 pulses, tc = workload(B, L, M, dtype, tau)
                 Fsum = torch.empty(B, dtype=dtype, device=dev)
                 G = torch.empty(B, L, 2, dtype=dtype, device=dev)
-                shapes = [(0, 0), (1, 1), (2, 1), (4, 1)] if dn == "f32" else [(0, 0), (1, 1), (2, 1)]
+                shapes = [(0, 0), (1, 1), (2, 1), (4, 1), (-2, 1), (-4, 1)] if dn == "f32" else [(0, 0), (1, 1), (2, 1)]
                 if B * M < 40000:
                     shapes += [(1, 2), (1, 4), (1, 8), (1, 16)]
                 for st, lps in shapes:
                     for fast in ((False, True) if dn == "f32" else (False,)):
                         if dn == "f64" and name == "curriculum" and st == 0:
                             continue
-                        flags = uq.tuning_flags(st=st, lps=lps, fast_sincos=fast)
+                        flags = uq.tuning_flags(st=abs(st), lps=lps, fast_sincos=fast, no_packed=st < 0)
                         fn = lambda: ops._launch_fwdbwd(pulses, tc, None, None, M, 0, (1.0, 0.05), 7, 0, None, None, Fsum, G, flags)
                         it = 5 if (dn == "f64" and name == "curriculum") else 10
                         best, mean = time_kernel(fn, iters=it)

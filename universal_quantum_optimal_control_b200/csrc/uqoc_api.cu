@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "uqoc_su2_kernels.cuh"
+#include "uqoc_su2_x2.cuh"
 
 namespace uqoc {
 
@@ -85,7 +86,9 @@ static Su2Plan make_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fl
     const int fsp = (flags >> 18) & 0xFFF;
     if (fsp) splits = fsp < plan.n_tiles ? fsp : plan.n_tiles;
     plan.splits = (int)splits;
-    plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd) : su2_smem_bytes<float>(lps, plan.C, bwd);
+    plan.packed = (dtype == UQOC_F32) && lps == 1 && st >= 2 && !(flags & UQOC_FLAG_NO_PACKED);
+    plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd)
+                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, bwd) : su2_smem_bytes<float>(lps, plan.C, bwd));
     return plan;
 }
 

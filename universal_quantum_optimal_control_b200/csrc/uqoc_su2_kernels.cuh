@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(128) su2_generator_bwd_kernel(const T* __restr
 struct Su2Plan {
     int st, lps, splits, n_tiles, C;
     size_t smem;
+    bool packed;   // FP32 only: f32x2 (FFMA2) kernel, two samples per register pair
 };
 
 }  // namespace uqoc

@@ -1,7 +1,9 @@
 // Template dispatch (ST, LPS, BWD) -> kernel launch.  Included by one translation unit per
 // (scalar type, sin/cos policy) so the 16 instantiations of each compile in parallel.
 #pragma once
+#include <type_traits>
 #include "uqoc_su2_kernels.cuh"
+#include "uqoc_su2_x2.cuh"
 
 namespace uqoc {
 
@@ -24,9 +26,29 @@ static int su2_launch_one(const Su2Params<T>& p, const Su2Plan& plan, cudaStream
     return launch_status("su2_kernel");
 }
 
+template <int NP, int SC, bool BWD>
+static int su2_launch_x2(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
+    auto kern = su2_kernel_x2<NP, SC, BWD>;
+    if (plan.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        if (e != cudaSuccess) {
+            set_error("su2 kernel needs %zu bytes of shared memory (L too large): %s", plan.smem, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return UQOC_E_UNSUPPORTED;
+        }
+    }
+    const unsigned grid = (unsigned)((long long)p.B * plan.splits);
+    kern<<<grid, kThreads, plan.smem, stream>>>(p);
+    return launch_status("su2_kernel_x2");
+}
+
 template <typename T, int SC, bool BWD>
 static int su2_launch_bwd(const Su2Params<T>& p, const Su2Plan& plan, cudaStream_t stream) {
     const int key = plan.st * 100 + plan.lps;
+    if constexpr (std::is_same<T, float>::value && SC != SC_LIBM) {
+        if (plan.packed && key == 201) return su2_launch_x2<1, SC, BWD>(p, plan, stream);
+        if (plan.packed && key == 401) return su2_launch_x2<2, SC, BWD>(p, plan, stream);
+    }
     switch (key) {
         case 101: return su2_launch_one<T, 1, 1, SC, BWD>(p, plan, stream);
         case 201: return su2_launch_one<T, 2, 1, SC, BWD>(p, plan, stream);

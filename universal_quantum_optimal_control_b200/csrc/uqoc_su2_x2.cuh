@@ -1,0 +1,361 @@
+// Packed-FP32 (f32x2 -> SASS FFMA2/FMUL2/FADD2, new on sm_100) variant of the fused SU(2) kernel.
+//
+// Two error samples ride in the two halves of every 64-bit register pair, so one instruction
+// advances two propagations.  The FP32 FMA pipe does the same FLOPs either way, but the packed
+// form needs half the issue slots and half the register-file reads per FLOP -- the scalar kernel
+// is issue/dispatch limited (ncu: 81 % issue-active, dispatch stalls from operand-bank conflicts),
+// this one is limited by the FMA pipe itself.  Same algorithm as su2_kernel (uqoc_su2_kernels.cuh),
+// LPS = 1 only (one thread owns its samples' whole pulse train).
+#pragma once
+#include "uqoc_su2_kernels.cuh"
+
+namespace uqoc {
+
+typedef unsigned long long u64;
+
+struct F2 {
+    u64 v;
+};
+
+__device__ __forceinline__ F2 f2(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ F2 f2b(float s) { return f2(s, s); }
+__device__ __forceinline__ float f2lo(F2 a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return lo;
+}
+__device__ __forceinline__ float f2hi(F2 a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return hi;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    F2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return d;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+    F2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+    F2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) {
+    F2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+// ptxas folds this into the consumer's operand-negate modifier (no instruction is emitted)
+__device__ __forceinline__ F2 neg2(F2 a) { return f2(-f2lo(a), -f2hi(a)); }
+
+// packed twin of sincos_modpi (uqoc_common.cuh): (s, c) = (-1)^k (sin h, cos h), k in kb_*.
+__device__ __forceinline__ void sincos_modpi2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_hi) {
+    const float MAGIC = 12582912.0f;
+    F2 kf = fma2(h, f2b(0.318309886183790672f), f2b(MAGIC));
+    kb_lo = __float_as_int(f2lo(kf));
+    kb_hi = __float_as_int(f2hi(kf));
+    kf = add2(kf, f2b(-MAGIC));
+    F2 r = fma2(kf, f2b(-3.14159274101257324f), h);
+    r = fma2(kf, f2b(8.74227765734758577e-08f), r);
+    const F2 z = mul2(r, r);
+    F2 ps = fma2(z, f2b(2.6325158160034334e-06f), f2b(-1.9822049944195896e-04f));
+    ps = fma2(z, ps, f2b(8.3332369104027748e-03f));
+    ps = fma2(z, ps, f2b(-1.6666665673255920e-01f));
+    const F2 rz = mul2(r, z);
+    s = fma2(rz, ps, r);
+    F2 pc = fma2(z, f2b(-2.6282461362825416e-07f), f2b(2.4774040866759606e-05f));
+    pc = fma2(z, pc, f2b(-1.3888647081330419e-03f));
+    pc = fma2(z, pc, f2b(4.1666660457849503e-02f));
+    pc = fma2(z, pc, f2b(-0.5f));
+    c = fma2(z, pc, f2b(1.0f));
+}
+
+template <int SC>
+__device__ __forceinline__ void sincos2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_hi) {
+    if constexpr (SC == SC_MUFU) {
+        float s0, c0, s1, c1;
+        __sincosf(f2lo(h), &s0, &c0);
+        __sincosf(f2hi(h), &s1, &c1);
+        s = f2(s0, s1);
+        c = f2(c0, c1);
+        kb_lo = kb_hi = 0;
+    } else {
+        sincos_modpi2(h, s, c, kb_lo, kb_hi);
+    }
+}
+
+// shared memory of one block of the packed kernel (bytes)
+__host__ __device__ inline size_t su2_x2_smem_bytes(int C, bool bwd) {
+    size_t bytes = (size_t)C * 16 + (size_t)C * 8;               // {c,c,s,s} rows + {tau,tau}
+    if (bwd) bytes += (size_t)C * 16;                            // {cd,cd,sd,sd} rows
+    if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);    // per-warp gradient accumulators
+    bytes += 32 * sizeof(float);
+    return bytes;
+}
+
+// NP = sample PAIRS per thread (1 or 2)
+template <int NP, int SC, bool BWD>
+__global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float> p) {
+    constexpr int ST = 2 * NP;
+    constexpr int NB = 8;
+    constexpr int TS = kThreads * ST;
+    constexpr int NV = 2 * NB;
+
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int C = p.C;
+    float4* fwd4 = reinterpret_cast<float4*>(smem_raw);
+    float4* bwd4 = fwd4 + C;
+    float2* tau2 = reinterpret_cast<float2*>(bwd4 + (BWD ? C : 0));
+    float* acc = reinterpret_cast<float*>(tau2 + C);
+    float* scratch = acc + (BWD ? (size_t)kWarps * C * 2 : 0);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int split = blockIdx.x % p.splits;
+    const int b = blockIdx.x / p.splits;
+    const int L = p.L;
+
+    {
+        const float* pb = p.pulses + (size_t)b * L * 2;
+        for (int i = tid; i < C; i += kThreads) {
+            const int ic = i < L ? i : L - 1;
+            const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
+            const double phi = (double)pb[2 * ic];
+            const double phim = (double)pb[2 * im];
+            const float tau = i < L ? pb[2 * ic + 1] : 0.0f;
+            double sn, cs;
+            ::sincos(phi, &sn, &cs);
+            fwd4[i] = make_float4((float)cs, (float)cs, (float)sn, (float)sn);
+            tau2[i] = make_float2(tau, tau);
+            if (BWD) {
+                double sd, cd;
+                ::sincos(i == 0 ? 0.0 : phi - phim, &sd, &cd);
+                bwd4[i] = make_float4((float)cd, (float)cd, (float)sd, (float)sd);
+            }
+        }
+        if (BWD) {
+            for (int i = tid; i < kWarps * C * 2; i += kThreads) acc[i] = 0.0f;
+        }
+    }
+    __syncthreads();
+
+    float cr[4], ci[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        cr[m] = p.target_c[(size_t)b * 8 + m];
+        ci[m] = p.target_c[(size_t)b * 8 + 4 + m];
+    }
+    const size_t Bm = (size_t)p.B * p.M;
+    float fsum = 0.0f;
+
+    for (int tile = split; tile < p.n_tiles; tile += p.splits) {
+        // ---- per-sample constants, packed pairwise: pair u = samples (2u, 2u+1) of this thread
+        F2 ka[NP], kr[NP], kr2[NP], kdl[NP], kae[NP];
+        bool valid[ST];
+        size_t sidx[ST];
+        {
+            SampleConst<float> kc[ST];
+#pragma unroll
+            for (int u = 0; u < ST; ++u) {
+                const long long j = (long long)tile * TS + u * kThreads + tid;
+                valid[u] = j < p.M;
+                sidx[u] = (size_t)b * p.M + (size_t)(valid[u] ? j : 0);
+                float delta = 0.0f, eps = 0.0f;
+                if (valid[u]) {
+                    if (p.err != nullptr) {
+                        delta = p.err[sidx[u]];
+                        eps = p.err[Bm + sidx[u]];
+                    } else {
+                        philox_delta_eps<float>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, delta, eps);
+                    }
+                    if (p.err_out != nullptr) {
+                        p.err_out[sidx[u]] = delta;
+                        p.err_out[Bm + sidx[u]] = eps;
+                    }
+                }
+                kc[u] = make_sample_const<float>(delta, eps);
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                ka[u] = f2(kc[2 * u].a, kc[2 * u + 1].a);
+                kr[u] = f2(kc[2 * u].r, kc[2 * u + 1].r);
+                kr2[u] = f2(kc[2 * u].r2, kc[2 * u + 1].r2);
+                kdl[u] = f2(kc[2 * u].delta, kc[2 * u + 1].delta);
+                kae[u] = f2(kc[2 * u].ae, kc[2 * u + 1].ae);
+            }
+        }
+
+        // ---------------- forward sweep ----------------
+        F2 Pa[NP], Pb[NP], Pc[NP], Pd[NP];
+        int par[ST];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            Pa[u] = f2b(1.0f);
+            Pb[u] = Pc[u] = Pd[u] = f2b(0.0f);
+            par[2 * u] = par[2 * u + 1] = 0;
+        }
+#pragma unroll 2
+        for (int jj = 0; jj < C; ++jj) {
+            const float4 row = fwd4[jj];
+            const float2 tt = tau2[jj];
+            const F2 cc = f2(row.x, row.y), ss = f2(row.z, row.w), tau = f2(tt.x, tt.y);
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                const F2 h = mul2(tau, ka[u]);
+                F2 s, c;
+                int k0, k1;
+                sincos2<SC>(h, s, c, k0, k1);
+                if (SC == SC_POLY && !BWD) {
+                    par[2 * u] ^= k0;
+                    par[2 * u + 1] ^= k1;
+                }
+                const F2 sp = mul2(s, kr[u]);
+                const F2 q1 = mul2(sp, cc), q2 = mul2(sp, ss), q3 = mul2(sp, kdl[u]);
+                const F2 oa = Pa[u], ob = Pb[u], oc = Pc[u], od = Pd[u];
+                Pa[u] = fma2(neg2(q3), od, fma2(neg2(q2), oc, fma2(neg2(q1), ob, mul2(c, oa))));
+                Pb[u] = fma2(neg2(q3), oc, fma2(q2, od, fma2(q1, oa, mul2(c, ob))));
+                Pc[u] = fma2(q3, ob, fma2(q2, oa, fma2(neg2(q1), od, mul2(c, oc))));
+                Pd[u] = fma2(q3, oa, fma2(neg2(q2), ob, fma2(q1, oc, mul2(c, od))));
+            }
+        }
+
+        // ---------------- fidelity epilogue (scalar, once per sample) ----------------
+        Quat<float> PL[ST];
+        float trr[ST], tri[ST];
+#pragma unroll
+        for (int u = 0; u < ST; ++u) {
+            const int pu = u >> 1;
+            Quat<float> q = (u & 1) ? Quat<float>{f2hi(Pa[pu]), f2hi(Pb[pu]), f2hi(Pc[pu]), f2hi(Pd[pu])}
+                                    : Quat<float>{f2lo(Pa[pu]), f2lo(Pb[pu]), f2lo(Pc[pu]), f2lo(Pd[pu])};
+            const float n2 = q.a * q.a + q.b * q.b + q.c * q.c + q.d * q.d;
+            const float inv = 1.0f / sqrtf(n2);
+            q.a *= inv; q.b *= inv; q.c *= inv; q.d *= inv;
+            PL[u] = q;
+            trr[u] = cr[0] * q.a + cr[1] * q.b + cr[2] * q.c + cr[3] * q.d;
+            tri[u] = ci[0] * q.a + ci[1] * q.b + ci[2] * q.c + ci[3] * q.d;
+            const float F = (trr[u] * trr[u] + tri[u] * tri[u] + 2.0f) * (1.0f / 6.0f);
+            if (valid[u]) {
+                fsum += F;
+                if (p.F_out != nullptr) p.F_out[sidx[u]] = F;
+                if (!BWD && p.U_out != nullptr) {
+                    const float sg = (par[u] & 1) ? -1.0f : 1.0f;
+                    float* U = p.U_out + sidx[u] * 8;
+                    U[0] = sg * q.a;  U[1] = -sg * q.d;
+                    U[2] = -sg * q.c; U[3] = -sg * q.b;
+                    U[4] = sg * q.c;  U[5] = -sg * q.b;
+                    U[6] = sg * q.a;  U[7] = sg * q.d;
+                }
+            }
+        }
+
+        if constexpr (BWD) {
+            // ---------------- adjoint seed ----------------
+            F2 A[NP], Bq[NP], W3[NP];
+            {
+                const float4 rowL = fwd4[C - 1];
+                float a_[ST], b_[ST], w_[ST];
+#pragma unroll
+                for (int u = 0; u < ST; ++u) {
+                    float wgt = 0.0f;
+                    if (valid[u]) wgt = p.weight != nullptr ? p.weight[sidx[u]] : 1.0f;
+                    const float fr = wgt * trr[u] * (1.0f / 3.0f), fi = wgt * tri[u] * (1.0f / 3.0f);
+                    const Quat<float> lam{fr * cr[0] + fi * ci[0], fr * cr[1] + fi * ci[1], fr * cr[2] + fi * ci[2],
+                                          fr * cr[3] + fi * ci[3]};
+                    const Quat<float> Wq = qmul(lam, qconj(PL[u]));
+                    a_[u] = Wq.b * rowL.x + Wq.c * rowL.z;
+                    b_[u] = Wq.c * rowL.x - Wq.b * rowL.z;
+                    w_[u] = Wq.d;
+                }
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    A[u] = f2(a_[2 * u], a_[2 * u + 1]);
+                    Bq[u] = f2(b_[2 * u], b_[2 * u + 1]);
+                    W3[u] = f2(w_[2 * u], w_[2 * u + 1]);
+                }
+            }
+            // ---------------- backward sweep ----------------
+            const F2 one = f2b(1.0f);
+            for (int jb = C / NB - 1; jb >= 0; --jb) {
+                float v[NV];
+#pragma unroll
+                for (int e = NB - 1; e >= 0; --e) {
+                    const float4 row = bwd4[jb * NB + e];
+                    const float2 tt = tau2[jb * NB + e];
+                    const F2 cd = f2(row.x, row.y), sd = f2(row.z, row.w), tau = f2(tt.x, tt.y);
+                    F2 gp = f2b(0.0f), gt = f2b(0.0f);
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        const F2 h = mul2(tau, ka[u]);
+                        F2 s, c;
+                        int k0, k1;
+                        sincos2<SC>(h, s, c, k0, k1);
+                        const F2 s2 = add2(s, s);
+                        const F2 C2 = fma2(neg2(s2), s, one);
+                        const F2 Sr = mul2(mul2(s2, kr[u]), c);
+                        const F2 k1_ = fma2(neg2(C2), kr2[u], kr2[u]);
+                        const F2 dl = kdl[u];
+                        const F2 t = fma2(dl, W3[u], A[u]);
+                        const F2 uu = fma2(dl, A[u], neg2(W3[u]));
+                        gt = fma2(kae[u], t, gt);
+                        gp = fma2(Sr, Bq[u], gp);
+                        gp = fma2(neg2(k1_), uu, gp);
+                        const F2 K = mul2(k1_, t), BS = mul2(Bq[u], Sr);
+                        F2 A1 = fma2(A[u], C2, K);
+                        A1 = fma2(dl, BS, A1);
+                        F2 B1 = mul2(Bq[u], C2);
+                        B1 = fma2(neg2(uu), Sr, B1);
+                        const F2 Wz = fma2(W3[u], C2, neg2(BS));
+                        W3[u] = fma2(dl, K, Wz);
+                        A[u] = fma2(neg2(B1), sd, mul2(A1, cd));
+                        Bq[u] = fma2(B1, cd, mul2(A1, sd));
+                    }
+                    v[2 * e] = f2lo(gp) + f2hi(gp);
+                    v[2 * e + 1] = f2lo(gt) + f2hi(gt);
+                }
+                int base = 0;
+                LaneReduce<float, NV, 1>::run(v, lane, base);
+                constexpr int NF = reduce_final_count(NV, 1);
+                constexpr int DUP = reduce_dup_mask(NV, 1);
+                if ((lane & DUP) == 0) {
+                    float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
+#pragma unroll
+                    for (int m = 0; m < NF; ++m) dst[m] += v[m];
+                }
+            }
+        }
+    }
+
+    {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+        if (lane == 0) scratch[warp] = fsum;
+    }
+    __syncthreads();
+    if (tid == 0 && p.Fsum_part != nullptr) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tot += scratch[w];
+        p.Fsum_part[(size_t)split * p.B + b] = tot;
+    }
+    if constexpr (BWD) {
+        float* gout = p.G_part + ((size_t)split * p.B + b) * L * 2;
+        const int LC2 = C * 2;
+        for (int i = tid; i < 2 * L; i += kThreads) {
+            float tot = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
+            gout[i] = (i & 1) ? tot : tot * 0.5f;
+        }
+    }
+}
+
+}  // namespace uqoc
