@@ -1,0 +1,67 @@
+"""Multi-GPU path (NCCL over NVLink): sample sharding + one all-reduce gives every rank the
+single-GPU loss and gradient.  Skipped on boxes with fewer than 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import universal_quantum_optimal_control_b200 as uq
+    g = torch.Generator().manual_seed(0)
+    B, L, M = 6, 40, 1001                         # M not divisible by world
+    pulses = torch.stack([(torch.rand(B, L, generator=g) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(B, L, generator=g)], -1)
+    ang = torch.rand(B, generator=g) * 3
+    X = torch.tensor([[0, 1], [1, 0]], dtype=torch.complex64)
+    T = torch.matrix_exp(-1j * X[None] * ang[:, None, None])
+    out = {}
+    for mode in ("philox", "explicit"):
+        err = None
+        if mode == "explicit":
+            err = torch.stack([torch.randn(B * M, generator=g), 0.05 * torch.randn(B * M, generator=g)]).to(dev)
+        p = pulses.to(dev).requires_grad_(True)
+        loss, mf = uq.fused_propagate_loss(p, T.to(dev), error=err, monte_carlo=M, sigma=(0.7, 0.05), seed=5, offset=3,
+                                           group=dist.group.WORLD)
+        loss.backward()
+        p1 = pulses.to(dev).requires_grad_(True)
+        loss1, mf1 = uq.fused_propagate_loss(p1, T.to(dev), error=err, monte_carlo=M, sigma=(0.7, 0.05), seed=5, offset=3)
+        loss1.backward()
+        out[mode] = (abs(loss.item() - loss1.item()) / abs(loss1.item()),
+                     ((p.grad - p1.grad).abs().max() / p1.grad.abs().max()).item(),
+                     (mf - mf1).abs().max().item())
+        # replicas must stay bit-identical: compare rank 0's gradient with everybody's
+        g0 = p.grad.clone()
+        dist.broadcast(g0, 0)
+        out[mode] += (bool(torch.equal(g0, p.grad)),)
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_fused_op_matches_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        for mode in ("philox", "explicit"):
+            dl, dg, dmf, same = ret[rank][mode]
+            assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6, (rank, mode, dl, dg, dmf)
+            assert same, (rank, mode)

@@ -59,8 +59,14 @@ def main():
                  ("shipped", 200, 100, 1000, (0.1, 0.5))]
         if "small" in which:
             cases += [("c1", 4, 16, 256, (0.1, 0.5)), ("mid", 64, 100, 1000, (0.1, 0.5))]
+        only = [w[5:] for w in which if w.startswith("case=")]
+        if only:
+            cases = [c for c in cases if c[0] in only]
+        f32only = "f32only" in which
         for name, B, L, M, tau in cases:
             for dtype, dn in ((torch.float32, "f32"), (torch.float64, "f64")):
+                if f32only and dn == "f64":
+                    continue
                 pulses, tc = workload(B, L, M, dtype, tau)
                 Fsum = torch.empty(B, dtype=dtype, device=dev)
                 G = torch.empty(B, L, 2, dtype=dtype, device=dev)

@@ -57,14 +57,16 @@ static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Choose samples/thread (ST), lanes/sample (LPS) and sample-tile splits per target.
 static Su2Plan make_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags, bool bwd) {
     const int sms = sm_count();
-    const int64_t N = B * M;                    // samples
-    const int64_t full = (int64_t)sms * 4 * 32 * 4;  // threads for 4 warps per sub-partition
+    const int64_t N = B * M;                         // samples
+    const int64_t one = (int64_t)sms * 4 * 32;       // threads for one warp per SM sub-partition
     int st = 1, lps = 1;
     const int st_max = (dtype == UQOC_F64) ? 2 : 4;
-    if (N >= 4 * full && st_max >= 4) st = 4;
-    else if (N >= 2 * full) st = 2;
-    if (N * 2 <= full) {
-        while (lps < 32 && lps * 2 <= L && N * lps * 2 <= full) lps *= 2;
+    // more samples per thread (packed f32x2 pairs, amortised staging/reduction) once every
+    // sub-partition still gets a warp; below that, split the pulse train over lanes instead
+    if (N >= 4 * one && st_max >= 4) st = 4;
+    else if (N >= 2 * one) st = 2;
+    if (N * 2 <= one) {
+        while (lps < 32 && lps * 2 <= L && N * lps * 2 <= 2 * one) lps *= 2;
     }
     const int fst = (flags >> 8) & 0xF, flps = (flags >> 12) & 0x3F;
     if (fst) st = fst;

@@ -92,6 +92,57 @@ __device__ __forceinline__ void sincos2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_
     }
 }
 
+// Stage-major evaluation for NP independent pairs: consecutive instructions are independent
+// (NP pairs x {sin, cos} Horner chains), which is what keeps the 2-cycle FFMA2 pipe fed from a
+// single warp instead of relying on other warps to hide each dependent-issue latency.
+template <int NP, int SC>
+__device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP]) {
+    if constexpr (SC == SC_MUFU) {
+#pragma unroll
+        for (int u = 0; u < NP; ++u) sincos2<SC>(h[u], s[u], c[u], kb[2 * u], kb[2 * u + 1]);
+    } else {
+        const float MAGIC = 12582912.0f;
+        F2 kf[NP], r[NP], z[NP], rz[NP], ps[NP], pc[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) kf[u] = fma2(h[u], f2b(0.318309886183790672f), f2b(MAGIC));
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            kb[2 * u] = __float_as_int(f2lo(kf[u]));
+            kb[2 * u + 1] = __float_as_int(f2hi(kf[u]));
+            kf[u] = add2(kf[u], f2b(-MAGIC));
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) r[u] = fma2(kf[u], f2b(-3.14159274101257324f), h[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) r[u] = fma2(kf[u], f2b(8.74227765734758577e-08f), r[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) z[u] = mul2(r[u], r[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            ps[u] = fma2(z[u], f2b(2.6325158160034334e-06f), f2b(-1.9822049944195896e-04f));
+            pc[u] = fma2(z[u], f2b(-2.6282461362825416e-07f), f2b(2.4774040866759606e-05f));
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            ps[u] = fma2(z[u], ps[u], f2b(8.3332369104027748e-03f));
+            pc[u] = fma2(z[u], pc[u], f2b(-1.3888647081330419e-03f));
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            rz[u] = mul2(r[u], z[u]);
+            ps[u] = fma2(z[u], ps[u], f2b(-1.6666665673255920e-01f));
+            pc[u] = fma2(z[u], pc[u], f2b(4.1666660457849503e-02f));
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            s[u] = fma2(rz[u], ps[u], r[u]);
+            pc[u] = fma2(z[u], pc[u], f2b(-0.5f));
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) c[u] = fma2(z[u], pc[u], f2b(1.0f));
+    }
+}
+
 // shared memory of one block of the packed kernel (bytes)
 __host__ __device__ inline size_t su2_x2_smem_bytes(int C, bool bwd) {
     size_t bytes = (size_t)C * 16 + (size_t)C * 8;               // {c,c,s,s} rows + {tau,tau}
@@ -208,24 +259,44 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
             const float4 row = fwd4[jj];
             const float2 tt = tau2[jj];
             const F2 cc = f2(row.x, row.y), ss = f2(row.z, row.w), tau = f2(tt.x, tt.y);
+            F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP], na[NP], nb[NP], nc[NP], nd[NP];
+            int kb[ST];
+#pragma unroll
+            for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
+            sincos2_n<NP, SC>(h, s, c, kb);
+            if (SC == SC_POLY && !BWD) {
+#pragma unroll
+                for (int u = 0; u < ST; ++u) par[u] ^= kb[u];
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) sp[u] = mul2(s[u], kr[u]);
 #pragma unroll
             for (int u = 0; u < NP; ++u) {
-                const F2 h = mul2(tau, ka[u]);
-                F2 s, c;
-                int k0, k1;
-                sincos2<SC>(h, s, c, k0, k1);
-                if (SC == SC_POLY && !BWD) {
-                    par[2 * u] ^= k0;
-                    par[2 * u + 1] ^= k1;
-                }
-                const F2 sp = mul2(s, kr[u]);
-                const F2 q1 = mul2(sp, cc), q2 = mul2(sp, ss), q3 = mul2(sp, kdl[u]);
-                const F2 oa = Pa[u], ob = Pb[u], oc = Pc[u], od = Pd[u];
-                Pa[u] = fma2(neg2(q3), od, fma2(neg2(q2), oc, fma2(neg2(q1), ob, mul2(c, oa))));
-                Pb[u] = fma2(neg2(q3), oc, fma2(q2, od, fma2(q1, oa, mul2(c, ob))));
-                Pc[u] = fma2(q3, ob, fma2(q2, oa, fma2(neg2(q1), od, mul2(c, oc))));
-                Pd[u] = fma2(q3, oa, fma2(neg2(q2), ob, fma2(q1, oc, mul2(c, od))));
+                q1[u] = mul2(sp[u], cc);
+                q2[u] = mul2(sp[u], ss);
+                q3[u] = mul2(sp[u], kdl[u]);
             }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                na[u] = mul2(c[u], Pa[u]); nb[u] = mul2(c[u], Pb[u]); nc[u] = mul2(c[u], Pc[u]); nd[u] = mul2(c[u], Pd[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                na[u] = fma2(neg2(q1[u]), Pb[u], na[u]); nb[u] = fma2(q1[u], Pa[u], nb[u]);
+                nc[u] = fma2(neg2(q1[u]), Pd[u], nc[u]); nd[u] = fma2(q1[u], Pc[u], nd[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                na[u] = fma2(neg2(q2[u]), Pc[u], na[u]); nb[u] = fma2(q2[u], Pd[u], nb[u]);
+                nc[u] = fma2(q2[u], Pa[u], nc[u]);       nd[u] = fma2(neg2(q2[u]), Pb[u], nd[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+                na[u] = fma2(neg2(q3[u]), Pd[u], na[u]); nb[u] = fma2(neg2(q3[u]), Pc[u], nb[u]);
+                nc[u] = fma2(q3[u], Pb[u], nc[u]);       nd[u] = fma2(q3[u], Pa[u], nd[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < NP; ++u) { Pa[u] = na[u]; Pb[u] = nb[u]; Pc[u] = nc[u]; Pd[u] = nd[u]; }
         }
 
         // ---------------- fidelity epilogue (scalar, once per sample) ----------------
@@ -292,31 +363,48 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
                     const float2 tt = tau2[jb * NB + e];
                     const F2 cd = f2(row.x, row.y), sd = f2(row.z, row.w), tau = f2(tt.x, tt.y);
                     F2 gp = f2b(0.0f), gt = f2b(0.0f);
+                    F2 h[NP], s[NP], c[NP], s2[NP], C2[NP], Sr[NP], k1_[NP], t[NP], uu[NP], K[NP], BS[NP], A1[NP], B1[NP], Wz[NP];
+                    int kb[ST];
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
+                    sincos2_n<NP, SC>(h, s, c, kb);
 #pragma unroll
                     for (int u = 0; u < NP; ++u) {
-                        const F2 h = mul2(tau, ka[u]);
-                        F2 s, c;
-                        int k0, k1;
-                        sincos2<SC>(h, s, c, k0, k1);
-                        const F2 s2 = add2(s, s);
-                        const F2 C2 = fma2(neg2(s2), s, one);
-                        const F2 Sr = mul2(mul2(s2, kr[u]), c);
-                        const F2 k1_ = fma2(neg2(C2), kr2[u], kr2[u]);
-                        const F2 dl = kdl[u];
-                        const F2 t = fma2(dl, W3[u], A[u]);
-                        const F2 uu = fma2(dl, A[u], neg2(W3[u]));
-                        gt = fma2(kae[u], t, gt);
-                        gp = fma2(Sr, Bq[u], gp);
-                        gp = fma2(neg2(k1_), uu, gp);
-                        const F2 K = mul2(k1_, t), BS = mul2(Bq[u], Sr);
-                        F2 A1 = fma2(A[u], C2, K);
-                        A1 = fma2(dl, BS, A1);
-                        F2 B1 = mul2(Bq[u], C2);
-                        B1 = fma2(neg2(uu), Sr, B1);
-                        const F2 Wz = fma2(W3[u], C2, neg2(BS));
-                        W3[u] = fma2(dl, K, Wz);
-                        A[u] = fma2(neg2(B1), sd, mul2(A1, cd));
-                        Bq[u] = fma2(B1, cd, mul2(A1, sd));
+                        s2[u] = add2(s[u], s[u]);
+                        t[u] = fma2(kdl[u], W3[u], A[u]);
+                        uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        C2[u] = fma2(neg2(s2[u]), s[u], one);
+                        Sr[u] = mul2(mul2(s2[u], kr[u]), c[u]);
+                        gt = fma2(kae[u], t[u], gt);
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        k1_[u] = fma2(neg2(C2[u]), kr2[u], kr2[u]);
+                        BS[u] = mul2(Bq[u], Sr[u]);
+                        B1[u] = mul2(Bq[u], C2[u]);
+                        gp = fma2(Sr[u], Bq[u], gp);
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        K[u] = mul2(k1_[u], t[u]);
+                        gp = fma2(neg2(k1_[u]), uu[u], gp);
+                        B1[u] = fma2(neg2(uu[u]), Sr[u], B1[u]);
+                        Wz[u] = fma2(W3[u], C2[u], neg2(BS[u]));
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        A1[u] = fma2(A[u], C2[u], K[u]);
+                        W3[u] = fma2(kdl[u], K[u], Wz[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) A1[u] = fma2(kdl[u], BS[u], A1[u]);
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        A[u] = fma2(neg2(B1[u]), sd, mul2(A1[u], cd));
+                        Bq[u] = fma2(B1[u], cd, mul2(A1[u], sd));
                     }
                     v[2 * e] = f2lo(gp) + f2hi(gp);
                     v[2 * e + 1] = f2lo(gt) + f2hi(gt);

@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import F32, F64, FLAG_FAST_SINCOS, LOSS_KINDS, check
+from .sharding import shard_errors, shard_range
 
 __all__ = [
     "fused_propagate_loss", "propagate_fidelity", "batched_unitary_generator", "fidelity",
@@ -195,19 +196,12 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     if group is not None:
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-    per = (M_total + world - 1) // world
-    j0 = min(rank * per, M_total)
-    M = min(per, M_total - j0)
-    if M <= 0:
-        raise ValueError("monte_carlo must be >= world size")
+    j0, M = shard_range(M_total, rank, world)
     if error is not None:
         _require_cuda(error, "error")
         if error.shape != (2, B * M_total):
             raise ValueError(f"'error' must have shape (2, {B * M_total}), got {tuple(error.shape)}")
-        e = error.to(rdt)
-        if world > 1:
-            e = e.view(2, B, M_total)[:, :, j0:j0 + M]
-        error = e.reshape(2, B * M).contiguous()
+        error = shard_errors(error.to(rdt), B, M_total, j0, M).contiguous()
     fl = flags | (FLAG_FAST_SINCOS if fast_sincos else 0)
     return _FusedPropagateLoss.apply(p, tc, error, M, j0, M_total, tuple(float(s) for s in sigma), int(seed), int(offset),
                                      loss, tau, k, fl, group, F_out, err_out)
