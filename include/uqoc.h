@@ -133,6 +133,27 @@ int uqoc_su2_generator_backward(const void* pulses, const void* err, const void*
                                 int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Two-qubit SU(4) twins.  NOT IN THE REFERENCE (README.md:86,122 promise train/two_qubit/, absent;
+ * fidelity() is already generic in d, SCORE.py:181-183).  Builder-defined contract:
+ *   pulses (B, L, 3) = [phi1, phi2, tau];  err (3, B*M) = [delta1; delta2; eps] or NULL => Philox
+ *   (delta1, eps from the first Box-Muller pair -- the SU(2) stream -- delta2 from the second);
+ *   H = 1/2 [cos phi1 XI + sin phi1 YI + cos phi2 IX + sin phi2 IY + delta1 ZI + delta2 IZ + J ZZ],
+ *   U_k = exp(-i H_k tau_k (1+eps));  target (B, 4, 4) complex;  F = (|Tr(U^dagger T)|^2 + 4)/20
+ *   G (B, L, 3) = sum_j weight * dF/d[phi1, phi2, tau];  U_out (B*M, 4, 4) complex.
+ * ------------------------------------------------------------------------ */
+int64_t uqoc_su4_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags);
+int uqoc_su4_fwdbwd(const void* pulses, const void* target, const void* err, const void* weight,
+                    int64_t B, int64_t L, int64_t M, int64_t j0, double J,
+                    double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                    void* F_out, void* err_out, void* Fsum, void* G,
+                    void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
+int uqoc_su4_forward(const void* pulses, const void* target, const void* err,
+                     int64_t B, int64_t L, int64_t M, int64_t j0, double J,
+                     double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                     void* U_out, void* F_out, void* err_out, void* Fsum,
+                     void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
  * Loss epilogue (SCORE.py:185-198 applied to the pooled mean, and the chain rule
  * of loss.backward() at trainer.py:90):
  *   Fbar = sum_b Fsum[b] / n_total;  loss_out[0] = loss(Fbar); loss_out[1] = Fbar;

@@ -322,6 +322,25 @@ def philox_errors(B, M, sigma_delta, sigma_eps, seed, offset, j0=0, dtype=np.flo
     return np.stack([delta.reshape(-1), eps.reshape(-1)]).astype(dtype)
 
 
+def philox_errors_su4(B, M, sigma_delta, sigma_eps, seed, offset, j0=0, dtype=np.float64):
+    """(delta1, delta2, eps) of the SU(4) kernels: first Box-Muller pair -> (delta1, eps) (the SU(2)
+    stream), second pair's cosine branch -> delta2.  Returns (3, B*M)."""
+    j = (np.arange(M, dtype=np.uint64) + np.uint64(j0))[None, :].repeat(B, axis=0)
+    b = np.arange(B, dtype=np.uint32)[:, None].repeat(M, axis=1)
+    ctr = np.stack([(j & np.uint64(0xFFFFFFFF)).astype(np.uint32), (j >> np.uint64(32)).astype(np.uint32), b,
+                    np.full((B, M), np.uint32(offset & 0xFFFFFFFF), dtype=np.uint32)], axis=-1)
+    key = np.empty((B, M, 2), dtype=np.uint32)
+    key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
+    key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    x = philox4x32_10(ctr, key)
+    u = (x.astype(np.float64) + 0.5) * 2.0 ** -32
+    r0, r1 = np.sqrt(-2.0 * np.log(u[..., 0])), np.sqrt(-2.0 * np.log(u[..., 2]))
+    d1 = sigma_delta * r0 * np.cos(2 * np.pi * u[..., 1])
+    eps = sigma_eps * r0 * np.sin(2 * np.pi * u[..., 1])
+    d2 = sigma_delta * r1 * np.cos(2 * np.pi * u[..., 3])
+    return np.stack([d1.reshape(-1), d2.reshape(-1), eps.reshape(-1)]).astype(dtype)
+
+
 # --------------------------------------------------------------------------
 # A9: two-qubit SU(4) path.  NOT IN THE REFERENCE -- builder-defined (SURVEY.md
 # §8a row A9), parity unpinned by the reference.  Same callable contract:
@@ -373,6 +392,14 @@ def su4_unitary_generator(pulses, error, J=1.0):
     for k in range(L):
         out = U[:, k] @ out
     return out
+
+
+def su4_loss_and_grad(pulses, U_target, error, M, J=1.0, loss="sharp", tau=0.99, k=100):
+    """Pooled-mean loss (SCORE.py:194 semantics with d = 4) and d loss / d pulses (B, L, 3)."""
+    Fsum, grad, F = su4_fidelity_sum_and_grad(pulses, U_target, error, M, J)
+    n = F.size
+    val, dval = loss_and_dloss(Fsum.sum() / n, loss, tau, k)
+    return val, dval / n * grad, F
 
 
 def su4_fidelity_sum_and_grad(pulses, U_target, error, M, J=1.0, fd_step=None):

@@ -1,0 +1,132 @@
+"""GPU tests of the two-qubit SU(4) path against oracle/uqoc_oracle.py::su4_*.  The reference has
+no two-qubit code: parity here is against the builder's own oracle (unpinned)."""
+import numpy as np
+import pytest
+import torch
+
+import universal_quantum_optimal_control_b200 as uq
+from oracle import uqoc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _case(seed, B, L, M, J=1.0, sd=1.0):
+    rng = np.random.default_rng(seed)
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
+    err = np.stack([rng.normal(0, sd, B * M), rng.normal(0, sd, B * M), rng.normal(0, 0.05, B * M)])
+    T = orc.su4_unitary_generator(np.stack([rng.uniform(-3, 3, (B, 5)), rng.uniform(-3, 3, (B, 5)), rng.uniform(0.3, 1.0, (B, 5))], -1),
+                                  np.zeros((3, B)), J)
+    return pulses, err, T
+
+
+@pytest.mark.parametrize("dtype,tolF,tolG", [(torch.float64, 1e-12, 1e-10), (torch.float32, 1e-5, 1e-4)])
+@pytest.mark.parametrize("L,M,splits", [(1, 5, 0), (7, 70, 0), (33, 130, 3), (128, 64, 0)])
+def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits):
+    B, J = 3, 0.8
+    pulses, err, T = _case(L, B, L, M, J)
+    if dtype == torch.float32:
+        pulses, err = pulses.astype(np.float32).astype(np.float64), err.astype(np.float32).astype(np.float64)
+    want_l, want_g, want_F = orc.su4_loss_and_grad(pulses, T, err, M, J, "sharp")
+    p = _t(pulses, dtype).requires_grad_(True)
+    F = torch.empty(B * M, dtype=dtype, device=DEV)
+    loss, mf = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err, dtype), monte_carlo=M, J=J, F_out=F,
+                                           flags=uq.tuning_flags(splits=splits))
+    loss.backward()
+    assert np.abs(F.cpu().numpy() - want_F).max() < tolF
+    assert abs(loss.item() - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
+    g = p.grad.cpu().numpy().astype(np.float64)
+    assert np.abs(g - want_g).max() / np.abs(want_g).max() < tolG
+    assert np.abs(mf.cpu().numpy() - want_F.reshape(B, M).mean(1)).max() < 10 * tolF
+
+
+def test_su4_general_target_and_large_detuning():
+    B, L, M, J = 2, 20, 40, 1.3
+    pulses, err, T = _case(3, B, L, M, J, sd=2.5)            # |delta| up to ~7: several squarings
+    rng = np.random.default_rng(9)
+    T = T + 0.3 * (rng.normal(size=T.shape) + 1j * rng.normal(size=T.shape))
+    want_l, want_g, want_F = orc.su4_loss_and_grad(pulses, T, err, M, J, "nll")
+    p = _t(pulses).requires_grad_(True)
+    F = torch.empty(B * M, dtype=torch.float64, device=DEV)
+    loss, _ = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err), monte_carlo=M, J=J, loss="nll", F_out=F)
+    loss.backward()
+    assert np.abs(F.cpu().numpy() - want_F).max() < 1e-11
+    assert abs(loss.item() - want_l) < 1e-11
+    assert np.abs(p.grad.cpu().numpy() - want_g).max() / np.abs(want_g).max() < 1e-10
+
+
+def test_su4_generator_and_generic_fidelity():
+    B, L, M, J = 1, 16, 50, 1.0
+    pulses, err, T = _case(4, B, L, M, J)
+    want_U = orc.su4_unitary_generator(np.repeat(pulses, M, 0), err, J)
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 3e-6)):
+        pl = _t(pulses, dtype)
+        U = uq.su4_unitary_generator(pl.expand(M, -1, -1), _t(err, dtype), J)          # shared pulse train
+        assert U.shape == (M, 4, 4)
+        assert np.abs(U.cpu().numpy() - want_U).max() < tol
+        U2 = uq.su4_unitary_generator(pl.expand(M, -1, -1).contiguous(), _t(err, dtype), J)   # per-sample rows
+        assert np.abs(U2.cpu().numpy() - want_U).max() < tol
+        F = uq.fidelity(U, _t(T).expand(M, -1, -1), 2)                                  # d = 4 (SCORE.py:181-183)
+        want_F = orc.fidelity(want_U, np.repeat(T, M, 0), 2)
+        assert np.abs(F.cpu().numpy() - want_F).max() < 10 * tol
+    # J = 0 factorises into two independent SU(2) propagators
+    U0 = uq.su4_unitary_generator(_t(pulses).expand(M, -1, -1), _t(err), 0.0).cpu().numpy()
+    p1 = np.repeat(pulses[:, :, [0, 2]], M, 0)
+    p2 = np.repeat(pulses[:, :, [1, 2]], M, 0)
+    # SU(2) oracle scales delta by (1+eps) like the SU(4) definition does
+    Ua = orc.batched_unitary_generator(p1, err[[0, 2]])
+    Ub = orc.batched_unitary_generator(p2, err[[1, 2]])
+    kron = np.einsum("bij,bkl->bikjl", Ua, Ub).reshape(M, 4, 4)
+    assert np.abs(U0 - kron).max() < 1e-12
+
+
+def test_su4_philox_stream_and_sharding():
+    B, M = 3, 500
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 3e-6)):
+        e = uq.philox_errors_su4(B, M, (0.7, 0.05), seed=77, offset=4, j0=9, dtype=dtype).cpu().numpy()
+        want = orc.philox_errors_su4(B, M, 0.7, 0.05, 77, 4, j0=9)
+        assert np.abs(e - want).max() < tol
+    # (delta1, eps) coincide with the SU(2) stream of the same (seed, offset, b, j)
+    e2 = uq.philox_errors(B, M, (0.7, 0.05), seed=77, offset=4, j0=9, dtype=torch.float64).cpu().numpy()
+    assert np.abs(e[[0, 2]] - e2).max() < 3e-6
+    pulses, _, T = _case(5, B, 12, M)
+    p = _t(pulses).requires_grad_(True)
+    err_out = torch.empty(3, B * M, dtype=torch.float64, device=DEV)
+    loss, _ = uq.fused_propagate_loss_su4(p, _t(T), monte_carlo=M, sigma=(0.7, 0.05), seed=77, offset=4, err_out=err_out)
+    loss.backward()
+    want_l, want_g, _ = orc.su4_loss_and_grad(pulses, T, err_out.cpu().numpy(), M, 1.0)
+    assert abs(loss.item() - want_l) < 1e-11
+    assert np.abs(p.grad.cpu().numpy() - want_g).max() / np.abs(want_g).max() < 1e-10
+
+
+def test_su4_config4_sized_properties():
+    """BASELINE config 4 shape (L=128, 32k eps): invariants + a sampled oracle check."""
+    torch.manual_seed(0)
+    B, L, M, J = 1, 128, 32768, 1.0
+    pulses = torch.stack([(torch.rand(B, L) * 2 - 1) * 3.15, (torch.rand(B, L) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(B, L)], -1).to(DEV)
+    CZ = torch.diag(torch.tensor([1, 1, 1, -1], dtype=torch.complex64)).to(DEV)[None]
+    p = pulses.clone().requires_grad_(True)
+    F = torch.empty(B * M, device=DEV)
+    err_out = torch.empty(3, B * M, device=DEV)
+    loss, mf = uq.fused_propagate_loss_su4(p, CZ, monte_carlo=M, J=J, seed=3, F_out=F, err_out=err_out)
+    loss.backward()
+    assert F.min().item() >= 0.2 - 1e-5 and F.max().item() <= 1 + 1e-5
+    g1 = p.grad.clone()
+    p.grad = None
+    loss2, _ = uq.fused_propagate_loss_su4(p, CZ, monte_carlo=M, J=J, seed=3)
+    loss2.backward()
+    assert torch.equal(g1, p.grad)                                   # deterministic
+    idx = np.arange(0, M, 512)
+    U = orc.su4_unitary_generator(np.repeat(pulses.cpu().numpy().astype(np.float64), len(idx), 0),
+                                  err_out.cpu().numpy()[:, idx].astype(np.float64), J)
+    want = orc.fidelity(U, np.repeat(CZ.cpu().numpy(), len(idx), 0), 2)
+    assert np.abs(F.cpu().numpy()[idx] - want).max() < 1e-5
+    p64 = pulses.double().requires_grad_(True)
+    l64, _ = uq.fused_propagate_loss_su4(p64, CZ, error=err_out.double(), monte_carlo=M, J=J)
+    l64.backward()
+    assert ((g1.double() - p64.grad).abs().max() / p64.grad.abs().max()).item() < 1e-4

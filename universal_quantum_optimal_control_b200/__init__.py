@@ -10,6 +10,9 @@ from .ops import (  # noqa: F401
     fidelity,
     fp32_peak_tflops,
     fused_propagate_loss,
+    fused_propagate_loss_su4,
+    philox_errors_su4,
+    su4_unitary_generator,
     get_ore_error_distribution,
     get_ore_ple_error_distribution,
     infidelity_loss,

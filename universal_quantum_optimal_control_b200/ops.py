@@ -30,6 +30,7 @@ __all__ = [
     "sharp_loss", "negative_log_loss", "infidelity_loss", "custom_loss",
     "get_ore_ple_error_distribution", "get_ore_error_distribution", "philox_errors",
     "target_coeffs", "tuning_flags", "fp32_peak_tflops",
+    "fused_propagate_loss_su4", "su4_unitary_generator", "philox_errors_su4",
 ]
 
 
@@ -414,3 +415,121 @@ def get_ore_error_distribution(batch_size: int, delta_std=1.0, *, device="cuda",
     """Drop-in for SCORE.py:154-155 (legacy 1-D ORE sampler)."""
     return get_ore_ple_error_distribution(batch_size, delta_std, 0.0, device=device, dtype=dtype, seed=seed,
                                           offset=offset)[0]
+
+
+# ----------------------------------------------------------------------------- two-qubit SU(4) path
+# NOT in the reference (README.md:86 promises it); builder-defined contract, see include/uqoc.h.
+def _su4_target(U_target: torch.Tensor, rdt: torch.dtype, B: int) -> torch.Tensor:
+    _require_cuda(U_target, "U_target")
+    if U_target.ndim != 3 or U_target.shape[-2:] != (4, 4) or U_target.shape[0] != B:
+        raise ValueError(f"'U_target' must have shape ({B}, 4, 4)")
+    cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+    return torch.view_as_real(U_target.to(cdt).resolve_conj().contiguous()).contiguous()
+
+
+def _su4_launch(bwd, pulses, tgt, error, weight, M, j0, J, sigma, seed, offset, U_out, F_out, err_out, Fsum, G, flags):
+    B, L, _ = pulses.shape
+    lib = _lib.lib()
+    dt = _dt(pulses)
+    ws_bytes = lib.uqoc_su4_workspace_bytes(B, L, M, dt, flags)
+    ws = _workspace(ws_bytes, pulses.device)
+    if bwd:
+        check(lib.uqoc_su4_fwdbwd(_ptr(pulses), _ptr(tgt), _ptr(error), _ptr(weight), B, L, M, j0, float(J), float(sigma[0]),
+                                  float(sigma[1]), seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws),
+                                  ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su4_fwdbwd")
+    else:
+        check(lib.uqoc_su4_forward(_ptr(pulses), _ptr(tgt), _ptr(error), B, L, M, j0, float(J), float(sigma[0]),
+                                   float(sigma[1]), seed, offset, _ptr(U_out), _ptr(F_out), _ptr(err_out), _ptr(Fsum),
+                                   _ptr(ws), ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su4_forward")
+
+
+class _FusedPropagateLossSU4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pulses, tgt, error, M, j0, M_total, J, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out):
+        B, L, _ = pulses.shape
+        need_grad = ctx.needs_input_grad[0]
+        buf = torch.empty(B + (B * L * 3 if need_grad else 0), dtype=pulses.dtype, device=pulses.device)
+        Fsum, G = buf[:B], (buf[B:] if need_grad else None)
+        _su4_launch(need_grad, pulses, tgt, error, None, M, j0, J, sigma, seed, offset, None, F_out, err_out, Fsum, G, flags)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
+        mean_fid = Fsum / M_total
+        if need_grad:
+            ctx.save_for_backward(G.view(B, L, 3))
+        ctx.mark_non_differentiable(mean_fid)
+        return loss_out[0], mean_fid
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_mean):
+        (G,) = ctx.saved_tensors
+        return (g_loss * G,) + (None,) * 16
+
+
+def fused_propagate_loss_su4(pulses: torch.Tensor, U_target: torch.Tensor, *, error: Optional[torch.Tensor] = None,
+                             monte_carlo: int, J: float = 1.0, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0,
+                             offset: int = 0, loss: str = "sharp", tau: float = 0.99, k: float = 100,
+                             dtype: Optional[torch.dtype] = None, flags: int = 0, group=None,
+                             F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None):
+    """Two-qubit twin of :func:`fused_propagate_loss`: pulses (B, L, 3) = [phi1, phi2, tau], U_target (B, 4, 4),
+    error (3, B*M) = [delta1; delta2; eps] or None (Philox), coupling ``J`` of the ZZ term."""
+    if pulses.ndim != 3 or pulses.shape[-1] != 3:
+        raise ValueError("'pulses' must have shape (B, L, 3)")
+    _require_cuda(pulses, "pulses")
+    if loss not in LOSS_KINDS:
+        raise ValueError(f"unknown loss {loss!r}; expected one of {sorted(LOSS_KINDS)}")
+    rdt = dtype or _real_dtype(pulses)
+    B = pulses.shape[0]
+    M_total = int(monte_carlo)
+    tgt = _su4_target(U_target, rdt, B)
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    j0, M = shard_range(M_total, rank, world)
+    if error is not None:
+        _require_cuda(error, "error")
+        if error.shape != (3, B * M_total):
+            raise ValueError(f"'error' must have shape (3, {B * M_total}), got {tuple(error.shape)}")
+        error = shard_errors(error.to(rdt), B, M_total, j0, M).contiguous()
+    return _FusedPropagateLossSU4.apply(pulses.to(rdt).contiguous(), tgt, error, M, j0, M_total, float(J),
+                                        tuple(float(x) for x in sigma), int(seed), int(offset), loss, tau, k, flags, group,
+                                        F_out, err_out)
+
+
+def su4_unitary_generator(pulses: torch.Tensor, error: torch.Tensor, J: float = 1.0) -> torch.Tensor:
+    """Two-qubit generator with the reference's calling convention: pulses (Bm, L, 3), error (3, Bm) ->
+    (Bm, 4, 4) complex.  Forward only.  ``expand``-ed (stride-0) pulses share one staged pulse train;
+    materialised per-sample rows are run one target per block (correct, not tuned)."""
+    if pulses.ndim != 3 or pulses.shape[-1] != 3:
+        raise ValueError("'pulses' must have shape (B, L, 3)")
+    _require_cuda(pulses, "pulses")
+    _require_cuda(error, "error")
+    Bm = pulses.shape[0]
+    if error.ndim != 2 or error.shape != (3, Bm):
+        raise ValueError(f"'error' must have shape (3, {Bm})")
+    rdt = torch.float64 if (pulses.dtype == torch.float64 or error.dtype == torch.float64) else torch.float32
+    cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+    U = torch.empty(Bm, 4, 4, 2, dtype=rdt, device=pulses.device)
+    err = error.to(rdt).contiguous()
+    if Bm > 1 and pulses.stride(0) == 0:
+        tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None], rdt, 1)
+        _su4_launch(False, pulses[0:1].to(rdt).contiguous(), tgt, err, None, Bm, 0, J, (0.0, 0.0), 0, 0, U, None, None, None,
+                    None, 0)
+    else:
+        tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None].expand(Bm, -1, -1), rdt, Bm)
+        _su4_launch(False, pulses.to(rdt).contiguous(), tgt, err, None, 1, 0, J, (0.0, 0.0), 0, 0, U, None, None, None, None, 0)
+    return torch.view_as_complex(U)
+
+
+def philox_errors_su4(B: int, M: int, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, offset: int = 0, j0: int = 0,
+                      device="cuda", dtype=torch.float32) -> torch.Tensor:
+    """(3, B*M) = [delta1; delta2; eps] of the SU(4) kernels' Philox stream (reported through err_out)."""
+    dev = torch.device(device)
+    pulses = torch.zeros(B, 1, 3, dtype=dtype, device=dev)
+    cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+    tgt = _su4_target(torch.eye(4, dtype=cdt, device=dev)[None].expand(B, -1, -1), dtype, B)
+    out = torch.empty(3, B * M, dtype=dtype, device=dev)
+    _su4_launch(False, pulses, tgt, None, None, M, j0, 0.0, sigma, seed, offset, None, None, out, None, None, 0)
+    return out
