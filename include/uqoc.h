@@ -119,6 +119,25 @@ int uqoc_su2_forward(const void* pulses, const void* target_c, const void* err,
                      int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Forward-only sweep drivers.
+ *  - grid: replaces visualize/util.py:231-249 (fidelity_contour_plot): the (2, Nd*Ne) error tensor
+ *    of meshgrid(ORE, PLE, indexing="ij").flatten() is never built; sample j uses
+ *    delta = axis_delta[j / n_eps], eps = axis_eps[j % n_eps].  The two axes must be ONE buffer
+ *    [axis_delta (n_delta) | axis_eps (n_eps)].  Outputs are (B * n_delta * n_eps).
+ *  - sigmas: replaces the 199-iteration Python loop of visualize/util.py:313-326
+ *    (plot_fidelity_by_std) / :288-298: target row b draws its M Philox samples with
+ *    (sigma_delta, sigma_eps) = sigma_table[b] (B, 2); pass the same pulse row B times.
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_forward_grid(const void* pulses, const void* target_c, const void* axis_delta, int64_t n_delta,
+                          const void* axis_eps, int64_t n_eps, int64_t B, int64_t L,
+                          void* U_out, void* F_out, void* Fsum,
+                          void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
+int uqoc_su2_forward_sigmas(const void* pulses, const void* target_c, const void* sigma_table,
+                            int64_t B, int64_t L, int64_t M, int64_t j0, uint64_t seed, uint64_t offset,
+                            void* F_out, void* Fsum,
+                            void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
  * Strict reference signature: one pulse row PER SAMPLE.
  *   replaces batched_unitary_generator (SCORE.py:77-145, grape.py:78-138)
  *   pulses (Bm, L, 2), err (2, Bm)  ->  U_out (Bm, 2, 2) complex

@@ -28,6 +28,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_su2_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
                                 _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
+    "uqoc_su2_forward_grid": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
+    "uqoc_su2_forward_sigmas": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_su2_generator_forward": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _uint, _vp]),
     "uqoc_su2_generator_backward": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _int, _uint, _vp]),
     "uqoc_su4_workspace_bytes": (_i64, [_i64, _i64, _i64, _int, _uint]),

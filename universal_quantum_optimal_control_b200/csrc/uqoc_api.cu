@@ -263,7 +263,7 @@ template <typename T>
 static int su2_run(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
                    int64_t M, int64_t j0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* U_out,
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
-                   unsigned flags, bool bwd, cudaStream_t stream) {
+                   unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr) {
     const Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
     Su2Params<T> p;
     p.pulses = (const T*)pulses;
@@ -276,6 +276,7 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     p.sig_d = (T)sig_d; p.sig_e = (T)sig_e;
     p.seed = seed; p.offset = (unsigned)offset;
     p.U_out = (T*)U_out; p.F_out = (T*)F_out; p.err_out = (T*)err_out;
+    p.grid_ne = grid_ne; p.sig_tab = (const T*)sig_tab;
     const int64_t n_g = bwd ? B * L * 2 : 0;
     if (plan.splits > 1) {
         const int64_t need = (int64_t)plan.splits * (B + n_g) * (int64_t)sizeof(T);
@@ -366,6 +367,39 @@ int uqoc_su2_forward(const void* pulses, const void* target_c, const void* err, 
                                Fsum, nullptr, workspace, workspace_bytes, dtype, flags, false, (cudaStream_t)stream);
     return su2_run<float>(pulses, target_c, err, nullptr, B, L, M, j0, sig_d, sig_e, seed, offset, U_out, F_out, err_out, Fsum,
                           nullptr, workspace, workspace_bytes, dtype, flags, false, (cudaStream_t)stream);
+}
+
+int uqoc_su2_forward_grid(const void* pulses, const void* target_c, const void* axis_delta, int64_t n_delta,
+                          const void* axis_eps, int64_t n_eps, int64_t B, int64_t L, void* U_out, void* F_out,
+                          void* Fsum, void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream) {
+    UQOC_CHECK_ARG(n_delta >= 1 && n_eps >= 1 && n_eps < (1LL << 31), "grid axes must be non-empty");
+    const int64_t M = n_delta * n_eps;
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && target_c && axis_delta && axis_eps, "null pointer");
+    UQOC_CHECK_ARG(U_out || F_out || Fsum, "no output requested");
+    const int64_t esz = dtype == UQOC_F64 ? 8 : 4;
+    UQOC_CHECK_ARG((const char*)axis_eps == (const char*)axis_delta + n_delta * esz,
+                   "axis_eps must directly follow axis_delta in one buffer [delta axis | eps axis]");
+    if (dtype == UQOC_F64)
+        return su2_run<double>(pulses, target_c, axis_delta, nullptr, B, L, M, 0, 0, 0, 0, 0, U_out, F_out, nullptr, Fsum,
+                               nullptr, workspace, workspace_bytes, dtype, flags, false, (cudaStream_t)stream, (int)n_eps);
+    return su2_run<float>(pulses, target_c, axis_delta, nullptr, B, L, M, 0, 0, 0, 0, 0, U_out, F_out, nullptr, Fsum, nullptr,
+                          workspace, workspace_bytes, dtype, flags, false, (cudaStream_t)stream, (int)n_eps);
+}
+
+int uqoc_su2_forward_sigmas(const void* pulses, const void* target_c, const void* sigma_table, int64_t B, int64_t L,
+                            int64_t M, int64_t j0, uint64_t seed, uint64_t offset, void* F_out, void* Fsum,
+                            void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream) {
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && target_c && sigma_table, "null pointer");
+    UQOC_CHECK_ARG(F_out || Fsum, "no output requested");
+    if (dtype == UQOC_F64)
+        return su2_run<double>(pulses, target_c, nullptr, nullptr, B, L, M, j0, 0, 0, seed, offset, nullptr, F_out, nullptr,
+                               Fsum, nullptr, workspace, workspace_bytes, dtype, flags, false, (cudaStream_t)stream, 0, sigma_table);
+    return su2_run<float>(pulses, target_c, nullptr, nullptr, B, L, M, j0, 0, 0, seed, offset, nullptr, F_out, nullptr, Fsum,
+                          nullptr, workspace, workspace_bytes, dtype, flags, false, (cudaStream_t)stream, 0, sigma_table);
 }
 
 int uqoc_su2_generator_forward(const void* pulses, const void* err, int64_t Bm, int64_t L, void* U_out, int dtype,

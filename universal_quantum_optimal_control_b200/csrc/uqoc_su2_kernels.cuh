@@ -38,7 +38,28 @@ struct Su2Params {
     T* err_out;    // (2, B*M) or nullptr
     T* Fsum_part;  // [splits][B]
     T* G_part;     // [splits][B][L][2]
+    // forward-only sweep modes (visualize/util.py:231-249, :313-326)
+    int grid_ne;          // > 0: err = [delta axis (M / grid_ne) | eps axis (grid_ne)], sample j -> (j / ne, j % ne)
+    const T* sig_tab;     // non-null: per-target (sigma_delta, sigma_eps) rows for the Philox samples
 };
+
+// (delta, eps) of sample (b, j): explicit tensor, 1-D axes of a meshgrid('ij') sweep, or on-chip Philox
+template <typename T>
+__device__ __forceinline__ void su2_sample_errors(const Su2Params<T>& p, int b, long long j, size_t sidx, size_t Bm,
+                                                  T& delta, T& eps) {
+    if (p.grid_ne > 0) {
+        const long long nd = p.M / p.grid_ne;
+        delta = p.err[j / p.grid_ne];
+        eps = p.err[nd + j % p.grid_ne];
+    } else if (p.err != nullptr) {
+        delta = p.err[sidx];
+        eps = p.err[Bm + sidx];
+    } else {
+        const T sd = p.sig_tab != nullptr ? p.sig_tab[2 * b] : p.sig_d;
+        const T se = p.sig_tab != nullptr ? p.sig_tab[2 * b + 1] : p.sig_e;
+        philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, sd, se, delta, eps);
+    }
+}
 
 // gradient-buffer depth: steps buffered in registers before one cross-lane reduction
 template <int LPS>
@@ -177,12 +198,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
             sidx[u] = (size_t)b * p.M + (size_t)(valid[u] ? j : 0);
             T delta = (T)0, eps = (T)0;
             if (valid[u]) {
-                if (p.err != nullptr) {
-                    delta = p.err[sidx[u]];
-                    eps = p.err[Bm + sidx[u]];
-                } else {
-                    philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, delta, eps);
-                }
+                su2_sample_errors<T>(p, b, j, sidx[u], Bm, delta, eps);
                 if (p.err_out != nullptr && k == 0) {
                     p.err_out[sidx[u]] = delta;
                     p.err_out[Bm + sidx[u]] = eps;

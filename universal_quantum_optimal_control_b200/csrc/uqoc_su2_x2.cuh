@@ -222,12 +222,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
                 sidx[u] = (size_t)b * p.M + (size_t)(valid[u] ? j : 0);
                 float delta = 0.0f, eps = 0.0f;
                 if (valid[u]) {
-                    if (p.err != nullptr) {
-                        delta = p.err[sidx[u]];
-                        eps = p.err[Bm + sidx[u]];
-                    } else {
-                        philox_delta_eps<float>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, delta, eps);
-                    }
+                    su2_sample_errors<float>(p, b, j, sidx[u], Bm, delta, eps);
                     if (p.err_out != nullptr) {
                         p.err_out[sidx[u]] = delta;
                         p.err_out[Bm + sidx[u]] = eps;
