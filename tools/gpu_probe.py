@@ -71,7 +71,7 @@ def main():
                 Fsum = torch.empty(B, dtype=dtype, device=dev)
                 G = torch.empty(B, L, 2, dtype=dtype, device=dev)
                 shapes = [(0, 0), (1, 1), (2, 1), (4, 1), (-2, 1), (-4, 1)] if dn == "f32" else [(0, 0), (1, 1), (2, 1)]
-                if B * M < 40000:
+                if B * M < 40000 or name == "grape":
                     shapes += [(1, 2), (1, 4), (1, 8), (1, 16)]
                 for st, lps in shapes:
                     for fast in ((False, True) if dn == "f32" else (False,)):
@@ -90,6 +90,32 @@ def main():
                     fn = lambda: ops._launch_forward(pulses, tc, None, M, 0, (1.0, 0.05), 7, 0, None, None, None, Fsum, flags)
                     best, mean = time_kernel(fn, iters=5)
                     emit(probe="sweep_fwd", case=name, dtype=dn, fast=fast, best_ms=best, gprops=B * M * L / best / 1e6)
+    if "su4" in which:
+        for dtype, dn in ((torch.float32, "f32"), (torch.float64, "f64")):
+            for (B, L, M) in ((1, 128, 32768), (8, 128, 32768)):
+                g = torch.Generator().manual_seed(0)
+                pulses = torch.stack([(torch.rand(B, L, generator=g) * 2 - 1) * 3.15, (torch.rand(B, L, generator=g) * 2 - 1) * 3.15,
+                                      0.1 + 0.4 * torch.rand(B, L, generator=g)], -1).to(dev, dtype)
+                cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+                tgt = ops._su4_target(torch.diag(torch.tensor([1, 1, 1, -1], dtype=cdt)).to(dev)[None].expand(B, -1, -1), dtype, B)
+                Fsum = torch.empty(B, dtype=dtype, device=dev)
+                G = torch.empty(B, L, 3, dtype=dtype, device=dev)
+                for bwd in (True, False):
+                    fn = lambda: ops._su4_launch(bwd, pulses, tgt, None, None, M, 0, 1.0, (1.0, 0.05), 7, 0, None, None, None, Fsum, G if bwd else None, 0)
+                    best, mean = time_kernel(fn, iters=5)
+                    emit(probe="su4", dtype=dn, B=B, L=L, M=M, bwd=bwd, best_ms=best, mprops=B * M * L / best / 1e3)
+    if "grid" in which:
+        from universal_quantum_optimal_control_b200 import sweeps
+        g = torch.Generator().manual_seed(0)
+        L = 64
+        pulse = torch.stack([(torch.rand(L, generator=g) * 2 - 1) * math.pi, 0.1 + 0.4 * torch.rand(L, generator=g)], -1).to(dev)
+        X = torch.tensor([[0, 1], [1, 0]], dtype=torch.complex64)
+        T = torch.matrix_exp(-1j * X * (math.pi / 4)).to(dev)
+        ore, ple = torch.linspace(-3, 3, 1000).to(dev), torch.linspace(-0.15, 0.15, 1000).to(dev)
+        for dtype, dn in ((torch.float32, "f32"), (torch.float64, "f64")):
+            fn = lambda: sweeps.fidelity_grid(pulse, T, ore, ple, dtype=dtype)
+            best, mean = time_kernel(fn, iters=10)
+            emit(probe="grid", dtype=dn, L=L, N=10 ** 6, best_ms=best, gprops=L * 1e6 / best / 1e6)
     if "acc" in which:
         for L, tau in ((16, (0.1, 0.5)), (64, (0.1, 0.5)), (100, (0.1, 0.5)), (256, (0.1, 0.5)), (256, (0.035, 0.07)), (400, (0.1, 0.5))):
             B, M = 8, 8192
