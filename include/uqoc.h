@@ -173,6 +173,20 @@ int uqoc_su4_forward(const void* pulses, const void* target, const void* err,
                      void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Pulse heads: the element-wise tail of the two pulse generators, fused to
+ * one launch each way.  ranges = {lo_phi, hi_phi, lo_tau, hi_tau} (HOST pointer, 4 doubles).
+ *  mode 0, logits (B, L, 2): model/universal_model.py:131-143
+ *      p = lo + (hi-lo) sigmoid(x); [p = scale*p + base_pulse (L,2)] (finetune, :135-138);
+ *      tau = relu(tau); phi = ((phi + phi_offset[b] + pi) mod 2pi) - pi          (:140-143)
+ *  mode 1, logits (B, L, 3): model/GRAPE_model.py:76-89
+ *      (ux,uy,ut) = sigmoid(x); phi = lo + (hi-lo) atan2(uy,ux); tau = relu(lo + (hi-lo) ut)
+ * ------------------------------------------------------------------------ */
+int uqoc_pulse_head_forward(const void* logits, const void* phi_offset, const void* base_pulse, int64_t B, int64_t L,
+                            int mode, const double* ranges, double scale, void* pulses, int dtype, void* stream);
+int uqoc_pulse_head_backward(const void* logits, const void* base_pulse, const void* grad_pulses, int64_t B, int64_t L,
+                             int mode, const double* ranges, double scale, void* grad_logits, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
  * Loss epilogue (SCORE.py:185-198 applied to the pooled mean, and the chain rule
  * of loss.backward() at trainer.py:90):
  *   Fbar = sum_b Fsum[b] / n_total;  loss_out[0] = loss(Fbar); loss_out[1] = Fbar;

@@ -258,6 +258,67 @@ __global__ void __launch_bounds__(256) sum_stage_kernel(const T* __restrict__ x,
     if (threadIdx.x == 0) out[blockIdx.x] = (T)red[0];
 }
 
+// ---- pulse heads: the element-wise tail of the pulse generators, one launch
+// each way instead of 6-8 ATen kernels.  mode 0 = transformer head (model/universal_model.py:131-143):
+//   u = sigmoid(x); p = lo + (hi-lo) u; [p = scale*p + base]; tau = relu(tau); phi = wrap(phi + offset_b)
+// mode 1 = GRAPE head (model/GRAPE_model.py:76-89): (ux,uy,ut) = sigmoid(x); phi_u = atan2(uy,ux);
+//   phi = lo0 + (hi0-lo0) phi_u; tau = relu(lo1 + (hi1-lo1) ut)
+template <typename T>
+struct HeadParams {
+    const T* x;        // (B, L, P_in)   P_in = 2 (mode 0) or 3 (mode 1)
+    const T* offset;   // (B) or nullptr   (mode 0: target azimuth added to phi)
+    const T* base;     // (L, 2) or nullptr (mode 0: finetune base pulse)
+    const T* gout;     // backward: (B, L, 2)
+    T* out;            // forward: (B, L, 2);  backward: (B, L, P_in)
+    long long n;       // B*L
+    int L, mode;
+    T lo0, hi0, lo1, hi1, scale;
+};
+template <typename T>
+__device__ __forceinline__ T sigmoid_t(T v) { return (T)1 / ((T)1 + exp(-v)); }
+
+template <typename T, bool BWD>
+__global__ void pulse_head_kernel(const HeadParams<T> p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const T PI = (T)3.14159265358979323846;
+    if (p.mode == 0) {
+        const T u0 = sigmoid_t(p.x[2 * i]), u1 = sigmoid_t(p.x[2 * i + 1]);
+        T phi = p.lo0 + (p.hi0 - p.lo0) * u0, tau = p.lo1 + (p.hi1 - p.lo1) * u1;
+        if (p.base != nullptr) {
+            const int l = (int)(i % p.L);
+            phi = p.scale * phi + p.base[2 * l];
+            tau = p.scale * tau + p.base[2 * l + 1];
+        }
+        if (!BWD) {
+            tau = tau > (T)0 ? tau : (T)0;
+            if (p.offset != nullptr) phi += p.offset[i / p.L];
+            // python's float modulo: (phi + pi) % (2 pi) - pi, result of % has the sign of the divisor
+            T m = fmod(phi + PI, (T)2 * PI);
+            if (m < (T)0) m += (T)2 * PI;
+            p.out[2 * i] = m - PI;
+            p.out[2 * i + 1] = tau;
+        } else {
+            const T sc = p.base != nullptr ? p.scale : (T)1;
+            p.out[2 * i] = p.gout[2 * i] * sc * (p.hi0 - p.lo0) * u0 * ((T)1 - u0);
+            p.out[2 * i + 1] = tau > (T)0 ? p.gout[2 * i + 1] * sc * (p.hi1 - p.lo1) * u1 * ((T)1 - u1) : (T)0;
+        }
+    } else {
+        const T ux = sigmoid_t(p.x[3 * i]), uy = sigmoid_t(p.x[3 * i + 1]), ut = sigmoid_t(p.x[3 * i + 2]);
+        const T tau = p.lo1 + (p.hi1 - p.lo1) * ut;
+        if (!BWD) {
+            p.out[2 * i] = p.lo0 + (p.hi0 - p.lo0) * atan2(uy, ux);
+            p.out[2 * i + 1] = tau > (T)0 ? tau : (T)0;
+        } else {
+            const T den = ux * ux + uy * uy;
+            const T gphi = p.gout[2 * i] * (p.hi0 - p.lo0) / den;
+            p.out[3 * i] = gphi * (-uy) * ux * ((T)1 - ux);
+            p.out[3 * i + 1] = gphi * ux * uy * ((T)1 - uy);
+            p.out[3 * i + 2] = tau > (T)0 ? p.gout[2 * i + 1] * (p.hi1 - p.lo1) * ut * ((T)1 - ut) : (T)0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ typed entry helpers
 template <typename T>
 static int su2_run(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
@@ -428,6 +489,36 @@ int uqoc_su2_generator_backward(const void* pulses, const void* err, const void*
     else
         su2_generator_bwd_kernel<float, SC_LIBM><<<blocks, 128, 0, (cudaStream_t)stream>>>((const float*)pulses, (const float*)err, (const float*)grad_U, Bm, (int)L, (float*)grad_pulses);
     return launch_status("su2_generator_bwd_kernel");
+}
+
+template <typename T, bool BWD>
+static int pulse_head_run(const void* x, const void* offset, const void* base, const void* gout, void* out, int64_t B,
+                          int64_t L, int mode, const double* ranges, double scale, cudaStream_t stream) {
+    HeadParams<T> p;
+    p.x = (const T*)x; p.offset = (const T*)offset; p.base = (const T*)base; p.gout = (const T*)gout; p.out = (T*)out;
+    p.n = B * L; p.L = (int)L; p.mode = mode;
+    p.lo0 = (T)ranges[0]; p.hi0 = (T)ranges[1]; p.lo1 = (T)ranges[2]; p.hi1 = (T)ranges[3]; p.scale = (T)scale;
+    const unsigned blocks = (unsigned)((p.n + 255) / 256);
+    pulse_head_kernel<T, BWD><<<blocks, 256, 0, stream>>>(p);
+    return launch_status("pulse_head_kernel");
+}
+
+int uqoc_pulse_head_forward(const void* logits, const void* phi_offset, const void* base_pulse, int64_t B, int64_t L,
+                            int mode, const double* ranges, double scale, void* pulses, int dtype, void* stream) {
+    UQOC_CHECK_ARG(logits && pulses && ranges, "null pointer");
+    UQOC_CHECK_ARG(B >= 1 && L >= 1 && (mode == 0 || mode == 1), "bad B/L/mode");
+    UQOC_CHECK_ARG(dtype == UQOC_F32 || dtype == UQOC_F64, "bad dtype %d", dtype);
+    if (dtype == UQOC_F64) return pulse_head_run<double, false>(logits, phi_offset, base_pulse, nullptr, pulses, B, L, mode, ranges, scale, (cudaStream_t)stream);
+    return pulse_head_run<float, false>(logits, phi_offset, base_pulse, nullptr, pulses, B, L, mode, ranges, scale, (cudaStream_t)stream);
+}
+
+int uqoc_pulse_head_backward(const void* logits, const void* base_pulse, const void* grad_pulses, int64_t B, int64_t L,
+                             int mode, const double* ranges, double scale, void* grad_logits, int dtype, void* stream) {
+    UQOC_CHECK_ARG(logits && grad_pulses && grad_logits && ranges, "null pointer");
+    UQOC_CHECK_ARG(B >= 1 && L >= 1 && (mode == 0 || mode == 1), "bad B/L/mode");
+    UQOC_CHECK_ARG(dtype == UQOC_F32 || dtype == UQOC_F64, "bad dtype %d", dtype);
+    if (dtype == UQOC_F64) return pulse_head_run<double, true>(logits, nullptr, base_pulse, grad_pulses, grad_logits, B, L, mode, ranges, scale, (cudaStream_t)stream);
+    return pulse_head_run<float, true>(logits, nullptr, base_pulse, grad_pulses, grad_logits, B, L, mode, ranges, scale, (cudaStream_t)stream);
 }
 
 int uqoc_loss_finalize(const void* Fsum, int64_t B, double n_total, int loss_kind, double tau, double k, void* G,
