@@ -375,6 +375,19 @@ static int check_common(int64_t B, int64_t L, int64_t M, int dtype) {
     return 0;
 }
 
+template <typename T, bool BWD>
+static int pulse_head_run(const void* x, const void* offset, const void* base, const void* gout, void* out, int64_t B,
+                          int64_t L, int mode, const double* ranges, double scale, cudaStream_t stream) {
+    HeadParams<T> p;
+    p.x = (const T*)x; p.offset = (const T*)offset; p.base = (const T*)base; p.gout = (const T*)gout; p.out = (T*)out;
+    p.n = B * L; p.L = (int)L; p.mode = mode;
+    p.lo0 = (T)ranges[0]; p.hi0 = (T)ranges[1]; p.lo1 = (T)ranges[2]; p.hi1 = (T)ranges[3]; p.scale = (T)scale;
+    const unsigned blocks = (unsigned)((p.n + 255) / 256);
+    pulse_head_kernel<T, BWD><<<blocks, 256, 0, stream>>>(p);
+    return launch_status("pulse_head_kernel");
+}
+
+
 }  // namespace uqoc
 
 using namespace uqoc;
@@ -489,18 +502,6 @@ int uqoc_su2_generator_backward(const void* pulses, const void* err, const void*
     else
         su2_generator_bwd_kernel<float, SC_LIBM><<<blocks, 128, 0, (cudaStream_t)stream>>>((const float*)pulses, (const float*)err, (const float*)grad_U, Bm, (int)L, (float*)grad_pulses);
     return launch_status("su2_generator_bwd_kernel");
-}
-
-template <typename T, bool BWD>
-static int pulse_head_run(const void* x, const void* offset, const void* base, const void* gout, void* out, int64_t B,
-                          int64_t L, int mode, const double* ranges, double scale, cudaStream_t stream) {
-    HeadParams<T> p;
-    p.x = (const T*)x; p.offset = (const T*)offset; p.base = (const T*)base; p.gout = (const T*)gout; p.out = (T*)out;
-    p.n = B * L; p.L = (int)L; p.mode = mode;
-    p.lo0 = (T)ranges[0]; p.hi0 = (T)ranges[1]; p.lo1 = (T)ranges[2]; p.hi1 = (T)ranges[3]; p.scale = (T)scale;
-    const unsigned blocks = (unsigned)((p.n + 255) / 256);
-    pulse_head_kernel<T, BWD><<<blocks, 256, 0, stream>>>(p);
-    return launch_status("pulse_head_kernel");
 }
 
 int uqoc_pulse_head_forward(const void* logits, const void* phi_offset, const void* base_pulse, int64_t B, int64_t L,
