@@ -363,3 +363,43 @@ def test_fast_sincos_mode_reports_accuracy():
     val, grad, F, _ = _fused(g["pulses"], g["U_target"], g["error"], int(g["M"]), torch.float32, fast=True)
     assert np.abs(F - g["F64"]).max() < 5e-4
     assert _relerr(grad, g["grad64"]) < 5e-3
+
+
+# ----------------------------------------------------------------------------- size limits / edge cases
+def test_long_pulse_train_uses_opt_in_shared_memory_and_rejects_beyond():
+    """L = 2000 needs > 48 KB of dynamic shared memory (opt-in path); an absurd L must fail loudly,
+    not silently fall back."""
+    from universal_quantum_optimal_control_b200._lib import UqocError
+    rng = np.random.default_rng(0)
+    B, L, M = 2, 2000, 64
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.01, 0.05, (B, L))], -1)
+    T = orc.batched_unitary_generator(pulses[:, :5], np.zeros((2, B)))
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)])
+    want_l, want_g, want_F = orc.loss_and_grad(pulses, T, err, M, "sharp")
+    for st in (1, 4):
+        val, grad, F, _ = _fused(pulses, T, err, M, torch.float64, flags=uq.tuning_flags(st=min(st, 2)))
+        assert np.abs(F - want_F).max() < 1e-11 and _relerr(grad, want_g) < 1e-10
+        val, grad, F, _ = _fused(pulses.astype(np.float32), T, err.astype(np.float32), M, torch.float32, flags=uq.tuning_flags(st=st))
+        assert np.abs(F - want_F).max() < 5e-5 and _relerr(grad, want_g) < 1e-3     # 2000 pulses of FP32 rounding
+    big = torch.zeros(1, 60000, 2, device=DEV)
+    with pytest.raises(UqocError, match="shared memory"):
+        uq.fused_propagate_loss(big.requires_grad_(True), _t(T[:1]), monte_carlo=8)
+
+
+@pytest.mark.parametrize("B,L,M", [(1, 1, 1), (1, 5, 1), (7, 3, 2), (1, 9, 33), (300, 4, 3)])
+def test_tiny_and_odd_shapes(B, L, M):
+    rng = np.random.default_rng(B * 100 + L * 10 + M)
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
+    T = orc.batched_unitary_generator(pulses[:, :1], np.zeros((2, B)))
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)])
+    want_l, want_g, want_F = orc.loss_and_grad(pulses, T, err, M, "infidelity")
+    val, grad, F, mf = _fused(pulses, T, err, M, torch.float64, loss="infidelity")
+    assert np.abs(F - want_F).max() < 1e-12 and abs(val - want_l) < 1e-12
+    assert np.abs(grad - want_g).max() < 1e-11 * max(1.0, np.abs(want_g).max())
+
+
+def test_empty_inputs_are_rejected():
+    with pytest.raises(Exception):
+        uq.fused_propagate_loss(torch.zeros(0, 4, 2, device=DEV), torch.zeros(0, 2, 2, dtype=torch.complex64, device=DEV), monte_carlo=4)
+    with pytest.raises(Exception):
+        uq.fused_propagate_loss(torch.zeros(2, 4, 2, device=DEV), torch.zeros(2, 2, 2, dtype=torch.complex64, device=DEV), monte_carlo=0)
