@@ -25,3 +25,4 @@ from .ops import (  # noqa: F401
 )
 
 __version__ = "0.1.0"
+from .graphs import GraphedFusedStep  # noqa: F401,E402

@@ -336,6 +336,7 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     p.j0 = j0;
     p.sig_d = (T)sig_d; p.sig_e = (T)sig_e;
     p.seed = seed; p.offset = (unsigned)offset;
+    p.rng_dev = (flags & UQOC_FLAG_RNG_FROM_DEVICE) ? (const unsigned long long*)(uintptr_t)seed : nullptr;
     p.U_out = (T*)U_out; p.F_out = (T*)F_out; p.err_out = (T*)err_out;
     p.grid_ne = grid_ne; p.sig_tab = (const T*)sig_tab;
     const int64_t n_g = bwd ? B * L * 2 : 0;

@@ -39,6 +39,7 @@ struct Su2Params {
     T* Fsum_part;  // [splits][B]
     T* G_part;     // [splits][B][L][2]
     // forward-only sweep modes (visualize/util.py:231-249, :313-326)
+    const unsigned long long* rng_dev;   // non-null: {seed, offset} read from device memory (CUDA-graph replay)
     int grid_ne;          // > 0: err = [delta axis (M / grid_ne) | eps axis (grid_ne)], sample j -> (j / ne, j % ne)
     const T* sig_tab;     // non-null: per-target (sigma_delta, sigma_eps) rows for the Philox samples
 };
@@ -57,7 +58,9 @@ __device__ __forceinline__ void su2_sample_errors(const Su2Params<T>& p, int b, 
     } else {
         const T sd = p.sig_tab != nullptr ? p.sig_tab[2 * b] : p.sig_d;
         const T se = p.sig_tab != nullptr ? p.sig_tab[2 * b + 1] : p.sig_e;
-        philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, sd, se, delta, eps);
+        const unsigned long long seed = p.rng_dev != nullptr ? p.rng_dev[0] : p.seed;
+        const unsigned offset = p.rng_dev != nullptr ? (unsigned)p.rng_dev[1] : p.offset;
+        philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, seed, offset, sd, se, delta, eps);
     }
 }
 
