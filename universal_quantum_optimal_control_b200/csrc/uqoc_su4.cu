@@ -120,36 +120,47 @@ __device__ __forceinline__ void su4_pulse_exp(M4<T>& E, T c1, T s1, T c2, T s2, 
         s = __reduce_max_sync(0xffffffffu, s);
     }
     const T sc = t * (T)0.5 / (T)(1 << s);         // Y = -i sc * (2H)
-    // Y = -i sc Hh,  Hh = 2H: diag (d1+d2+J, d1-d2-J, -d1+d2-J, -d1-d2+J), off-diagonals e^{-/+ i phi}
-    M4<T> Y;
+    // Y = -i sc Hh,  Hh = 2H = diag(d1+d2+J, d1-d2-J, -d1+d2-J, -d1-d2+J) + phase blocks.  Y has 12 non-zeros:
+    // a purely imaginary diagonal i*dg[] and four distinct off-diagonal values
+    //   a2 = -i sc e^{-i phi2} at (0,1),(2,3);  b2 = -i sc e^{+i phi2} at (1,0),(3,2)
+    //   a1 = -i sc e^{-i phi1} at (0,2),(1,3);  b1 = -i sc e^{+i phi1} at (2,0),(3,1)
+    const T dg0 = -sc * (k.d1 + k.d2 + J), dg1 = -sc * (k.d1 - k.d2 - J), dg2 = -sc * (-k.d1 + k.d2 - J),
+            dg3 = -sc * (-k.d1 - k.d2 + J);
+    const T a2r = -sc * s2, b2r = sc * s2, o2i = -sc * c2;     // a2 = a2r + i o2i, b2 = b2r + i o2i
+    const T a1r = -sc * s1, b1r = sc * s1, o1i = -sc * c1;
+    // Horner: E = I + Y/1 (I + Y/2 (I + ... (I + Y/DEG))), every step a SPARSE product Y*E (160 FMA, not 256)
+    {
+        const T inv = (T)(1.0 / DEG);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) Y.re[i] = Y.im[i] = (T)0;
-    Y.im[0] = -sc * (k.d1 + k.d2 + J);
-    Y.im[5] = -sc * (k.d1 - k.d2 - J);
-    Y.im[10] = -sc * (-k.d1 + k.d2 - J);
-    Y.im[15] = -sc * (-k.d1 - k.d2 + J);
-    // -i (c - i s) = -s - i c  (upper, e^{-i phi});   -i (c + i s) = s - i c  (lower, e^{+i phi})
-    const T a2r = -sc * s2, a2i = -sc * c2, b2r = sc * s2;
-    const T a1r = -sc * s1, a1i = -sc * c1, b1r = sc * s1;
-    Y.re[1] = a2r;  Y.im[1] = a2i;   // (0,1) e^{-i phi2}
-    Y.re[4] = b2r;  Y.im[4] = a2i;   // (1,0) e^{+i phi2}
-    Y.re[11] = a2r; Y.im[11] = a2i;  // (2,3)
-    Y.re[14] = b2r; Y.im[14] = a2i;  // (3,2)
-    Y.re[2] = a1r;  Y.im[2] = a1i;   // (0,2) e^{-i phi1}
-    Y.re[8] = b1r;  Y.im[8] = a1i;   // (2,0)
-    Y.re[7] = a1r;  Y.im[7] = a1i;   // (1,3)
-    Y.re[13] = b1r; Y.im[13] = a1i;  // (3,1)
-    // Horner: E = I + Y/1 (I + Y/2 (I + ... (I + Y/DEG)))
+        for (int i = 0; i < 16; ++i) E.re[i] = E.im[i] = (T)0;
+        E.re[0] = E.re[5] = E.re[10] = E.re[15] = (T)1;
+        E.im[0] = dg0 * inv; E.im[5] = dg1 * inv; E.im[10] = dg2 * inv; E.im[15] = dg3 * inv;
+        E.re[1] = a2r * inv;  E.im[1] = o2i * inv;   E.re[11] = a2r * inv; E.im[11] = o2i * inv;
+        E.re[4] = b2r * inv;  E.im[4] = o2i * inv;   E.re[14] = b2r * inv; E.im[14] = o2i * inv;
+        E.re[2] = a1r * inv;  E.im[2] = o1i * inv;   E.re[7] = a1r * inv;  E.im[7] = o1i * inv;
+        E.re[8] = b1r * inv;  E.im[8] = o1i * inv;   E.re[13] = b1r * inv; E.im[13] = o1i * inv;
+    }
     M4<T> Tm;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        E.re[i] = Y.re[i] * (T)(1.0 / DEG) + ((i % 5 == 0) ? (T)1 : (T)0);
-        E.im[i] = Y.im[i] * (T)(1.0 / DEG);
-    }
-#pragma unroll
     for (int d = DEG - 1; d >= 1; --d) {
-        m4_mul(Tm, Y, E);
         const T inv = (T)(1.0 / d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const T e0r = E.re[j], e0i = E.im[j], e1r = E.re[4 + j], e1i = E.im[4 + j];
+            const T e2r = E.re[8 + j], e2i = E.im[8 + j], e3r = E.re[12 + j], e3i = E.im[12 + j];
+            // row0 = i dg0 E0 + a2 E1 + a1 E2
+            Tm.re[j] = -dg0 * e0i + (a2r * e1r - o2i * e1i) + (a1r * e2r - o1i * e2i);
+            Tm.im[j] = dg0 * e0r + (a2r * e1i + o2i * e1r) + (a1r * e2i + o1i * e2r);
+            // row1 = b2 E0 + i dg1 E1 + a1 E3
+            Tm.re[4 + j] = (b2r * e0r - o2i * e0i) - dg1 * e1i + (a1r * e3r - o1i * e3i);
+            Tm.im[4 + j] = (b2r * e0i + o2i * e0r) + dg1 * e1r + (a1r * e3i + o1i * e3r);
+            // row2 = b1 E0 + i dg2 E2 + a2 E3
+            Tm.re[8 + j] = (b1r * e0r - o1i * e0i) - dg2 * e2i + (a2r * e3r - o2i * e3i);
+            Tm.im[8 + j] = (b1r * e0i + o1i * e0r) + dg2 * e2r + (a2r * e3i + o2i * e3r);
+            // row3 = b1 E1 + b2 E2 + i dg3 E3
+            Tm.re[12 + j] = (b1r * e1r - o1i * e1i) + (b2r * e2r - o2i * e2i) - dg3 * e3i;
+            Tm.im[12 + j] = (b1r * e1i + o1i * e1r) + (b2r * e2i + o2i * e2r) + dg3 * e3r;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             E.re[i] = Tm.re[i] * inv + ((i % 5 == 0) ? (T)1 : (T)0);
