@@ -46,6 +46,7 @@ extern "C" {
 #define UQOC_FLAG_NO_PACKED 2u   /* FP32 only: scalar FFMA kernel instead of the packed f32x2 (FFMA2) one */
 #define UQOC_FLAG_RNG_FROM_DEVICE 8u /* `seed` is a DEVICE pointer to uint64 {seed, offset}: lets a captured CUDA
                                        graph draw fresh Philox samples on every replay (offset argument ignored) */
+#define UQOC_FLAG_NO_TABLE 4u    /* packed kernel: polynomial sin/cos instead of the shared-memory table */
 /* tuning overrides (0 = let the library choose): samples per thread (1,2,4) and lanes per
  * sample (1,2,4,8,16,32) of the shared-pulse kernels */
 #define UQOC_FLAG_ST(n) (((unsigned)(n) & 0xFu) << 8)

@@ -89,8 +89,9 @@ static Su2Plan make_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fl
     if (fsp) splits = fsp < plan.n_tiles ? fsp : plan.n_tiles;
     plan.splits = (int)splits;
     plan.packed = (dtype == UQOC_F32) && lps == 1 && st >= 2 && !(flags & UQOC_FLAG_NO_PACKED);
+    plan.table = plan.packed && !(flags & UQOC_FLAG_FAST_SINCOS) && !(flags & UQOC_FLAG_NO_TABLE);
     plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd)
-                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, bwd) : su2_smem_bytes<float>(lps, plan.C, bwd));
+                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, bwd, plan.table) : su2_smem_bytes<float>(lps, plan.C, bwd));
     return plan;
 }
 

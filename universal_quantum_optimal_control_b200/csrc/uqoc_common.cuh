@@ -33,7 +33,7 @@ inline int launch_status(const char* what) {
 }
 
 // ---------------------------------------------------------------- sincos policies
-enum SinCosPolicy { SC_POLY = 0, SC_MUFU = 1, SC_LIBM = 2 };
+enum SinCosPolicy { SC_POLY = 0, SC_MUFU = 1, SC_LIBM = 2, SC_TABLE = 3 };
 
 // Accurate FP32 sin/cos of h reduced modulo PI (not 2 PI): returns (s, c) = (-1)^k (sin h,
 // cos h) and k in the low bits of `kbits`.  The common sign is irrelevant to the fidelity and

@@ -503,6 +503,7 @@ struct Su2Plan {
     int st, lps, splits, n_tiles, C;
     size_t smem;
     bool packed;   // FP32 only: f32x2 (FFMA2) kernel, two samples per register pair
+    bool table;    // packed kernel: table-lookup sin/cos instead of the polynomial pair
 };
 
 }  // namespace uqoc

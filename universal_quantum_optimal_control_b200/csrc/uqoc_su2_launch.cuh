@@ -46,6 +46,10 @@ template <typename T, int SC, bool BWD>
 static int su2_launch_bwd(const Su2Params<T>& p, const Su2Plan& plan, cudaStream_t stream) {
     const int key = plan.st * 100 + plan.lps;
     if constexpr (std::is_same<T, float>::value && SC != SC_LIBM) {
+        if constexpr (SC == SC_POLY) {
+            if (plan.packed && plan.table && key == 201) return su2_launch_x2<1, SC_TABLE, BWD>(p, plan, stream);
+            if (plan.packed && plan.table && key == 401) return su2_launch_x2<2, SC_TABLE, BWD>(p, plan, stream);
+        }
         if (plan.packed && key == 201) return su2_launch_x2<1, SC, BWD>(p, plan, stream);
         if (plan.packed && key == 401) return su2_launch_x2<2, SC, BWD>(p, plan, stream);
     }

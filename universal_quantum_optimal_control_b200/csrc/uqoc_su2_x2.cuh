@@ -11,6 +11,9 @@
 
 namespace uqoc {
 
+#include "uqoc_sincos_table.inc"
+constexpr int kTabN = UQOC_SINCOS_TABLE_N;
+
 typedef unsigned long long u64;
 
 struct F2 {
@@ -95,9 +98,41 @@ __device__ __forceinline__ void sincos2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_
 // Stage-major evaluation for NP independent pairs: consecutive instructions are independent
 // (NP pairs x {sin, cos} Horner chains), which is what keeps the 2-cycle FFMA2 pipe fed from a
 // single warp instead of relying on other warps to hide each dependent-issue latency.
+// SC_TABLE: h = k pi/N + r with |r| <= pi/2N (N = 1024).  (sin, cos)(k pi/N) come from a shared-memory
+// table (one LDS.32 per half), the residual is applied to FIRST order, (s, c) = (st + r ct, ct - r st):
+// the angle error is r^3/3 <= 1.2e-9; the norm error r^2/2 <= 1.2e-6 is radial (removed exactly by the
+// final re-normalisation of P_L) and has zero mean because the table is pre-scaled by 1 - (pi/2N)^2/6.
+// 6 FMA-pipe instructions (4 with immediates) instead of 14; the sign (-1)^(k div N) is dropped like in
+// the polynomial path (kb returns k >> 10 so the U_out kernel can track it).
 template <int NP, int SC>
-__device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP]) {
-    if constexpr (SC == SC_MUFU) {
+__device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
+                                          const float* __restrict__ tsin, const float* __restrict__ tcos) {
+    if constexpr (SC == SC_TABLE) {
+        const float MAGIC = 12582912.0f;
+        F2 kf[NP], r[NP], st[NP], ct[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) kf[u] = fma2(h[u], f2b(325.94931f), f2b(MAGIC));
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const int k0 = __float_as_int(f2lo(kf[u])), k1 = __float_as_int(f2hi(kf[u]));
+            kb[2 * u] = k0 >> 10;
+            kb[2 * u + 1] = k1 >> 10;
+            const int i0 = k0 & (kTabN - 1), i1 = k1 & (kTabN - 1);
+            st[u] = f2(tsin[i0], tsin[i1]);
+            ct[u] = f2(tcos[i0], tcos[i1]);
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) kf[u] = add2(kf[u], f2b(-MAGIC));
+#pragma unroll
+        for (int u = 0; u < NP; ++u) r[u] = fma2(kf[u], f2b(-0.003067961661145091f), h[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) r[u] = fma2(kf[u], f2b(8.537380524753502e-11f), r[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            s[u] = fma2(r[u], ct[u], st[u]);
+            c[u] = fma2(neg2(r[u]), st[u], ct[u]);
+        }
+    } else if constexpr (SC == SC_MUFU) {
 #pragma unroll
         for (int u = 0; u < NP; ++u) sincos2<SC>(h[u], s[u], c[u], kb[2 * u], kb[2 * u + 1]);
     } else {
@@ -144,8 +179,9 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
 }
 
 // shared memory of one block of the packed kernel (bytes)
-__host__ __device__ inline size_t su2_x2_smem_bytes(int C, bool bwd) {
+__host__ __device__ inline size_t su2_x2_smem_bytes(int C, bool bwd, bool table) {
     size_t bytes = (size_t)C * 16 + (size_t)C * 8;               // {c,c,s,s} rows + {tau,tau}
+    if (table) bytes += 2 * (size_t)UQOC_SINCOS_TABLE_N * sizeof(float);
     if (bwd) bytes += (size_t)C * 16;                            // {cd,cd,sd,sd} rows
     if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);    // per-warp gradient accumulators
     bytes += 32 * sizeof(float);
@@ -167,6 +203,8 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
     float2* tau2 = reinterpret_cast<float2*>(bwd4 + (BWD ? C : 0));
     float* acc = reinterpret_cast<float*>(tau2 + C);
     float* scratch = acc + (BWD ? (size_t)kWarps * C * 2 : 0);
+    float* tsin = scratch + 32;
+    float* tcos = tsin + kTabN;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -195,6 +233,12 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
         }
         if (BWD) {
             for (int i = tid; i < kWarps * C * 2; i += kThreads) acc[i] = 0.0f;
+        }
+        if (SC == SC_TABLE) {
+            for (int i = tid; i < kTabN; i += kThreads) {
+                tsin[i] = g_sin_table[i];
+                tcos[i] = g_cos_table[i];
+            }
         }
     }
     __syncthreads();
@@ -258,8 +302,8 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
             int kb[ST];
 #pragma unroll
             for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
-            sincos2_n<NP, SC>(h, s, c, kb);
-            if (SC == SC_POLY && !BWD) {
+            sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
+            if ((SC == SC_POLY || SC == SC_TABLE) && !BWD) {
 #pragma unroll
                 for (int u = 0; u < ST; ++u) par[u] ^= kb[u];
             }
@@ -362,7 +406,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float>
                     int kb[ST];
 #pragma unroll
                     for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
-                    sincos2_n<NP, SC>(h, s, c, kb);
+                    sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
 #pragma unroll
                     for (int u = 0; u < NP; ++u) {
                         s2[u] = add2(s[u], s[u]);

@@ -73,9 +73,10 @@ def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:
     return buf
 
 
-def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool = False, no_packed: bool = False) -> int:
+def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool = False, no_packed: bool = False,
+                 no_table: bool = False) -> int:
     """Pack the launch-shape overrides of include/uqoc.h (0 = library heuristic)."""
-    return ((FLAG_FAST_SINCOS if fast_sincos else 0) | (2 if no_packed else 0) | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
+    return ((FLAG_FAST_SINCOS if fast_sincos else 0) | (2 if no_packed else 0) | (4 if no_table else 0) | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
             | ((splits & 0xFFF) << 18))
 
 
