@@ -189,8 +189,11 @@ __host__ __device__ inline size_t su2_x2_smem_bytes(int C, bool bwd, bool table)
 }
 
 // NP = sample PAIRS per thread (1 or 2)
+// resident-block hint: the table kernel has LDS latency to hide, 6 blocks/SM (<= 80 registers) measured best
+constexpr int x2_min_blocks(int NP, int SC) { return (SC == SC_TABLE) ? 6 : 1; }
+
 template <int NP, int SC, bool BWD>
-__global__ void __launch_bounds__(kThreads) su2_kernel_x2(const Su2Params<float> p) {
+__global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2(const Su2Params<float> p) {
     constexpr int ST = 2 * NP;
     constexpr int NB = 8;
     constexpr int TS = kThreads * ST;
