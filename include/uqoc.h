@@ -47,6 +47,8 @@ extern "C" {
 #define UQOC_FLAG_RNG_FROM_DEVICE 8u /* `seed` is a DEVICE pointer to uint64 {seed, offset}: lets a captured CUDA
                                        graph draw fresh Philox samples on every replay (offset argument ignored) */
 #define UQOC_FLAG_NO_TABLE 4u    /* packed kernel: polynomial sin/cos instead of the shared-memory table */
+#define UQOC_FLAG_WPS4 16u       /* packed kernel: force the pulse train to be split over the block's 4 warps */
+#define UQOC_FLAG_WPS1 32u       /* packed kernel: force one warp per sample group */
 /* tuning overrides (0 = let the library choose): samples per thread (1,2,4) and lanes per
  * sample (1,2,4,8,16,32) of the shared-pulse kernels */
 #define UQOC_FLAG_ST(n) (((unsigned)(n) & 0xFu) << 8)
@@ -107,6 +109,20 @@ int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, c
                     void* F_out, void* err_out, void* Fsum, void* G,
                     void* workspace, int64_t workspace_bytes,
                     int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Single-GPU training step in one call: uqoc_su2_fwdbwd followed by the loss epilogue of
+ * uqoc_loss_finalize (n_total = B*M), with the partials reduction and the epilogue fused into one
+ * kernel when a target's samples are split over blocks.  The whole of trainer.py:80-90 between the
+ * model forward and the model backward in at most two launches.  loss_out = {loss, Fbar, dloss/dFbar};
+ * G comes back already scaled (= d loss / d pulses).
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* err,
+                         int64_t B, int64_t L, int64_t M,
+                         double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                         int loss_kind, double tau, double k,
+                         void* F_out, void* err_out, void* Fsum, void* G, void* loss_out,
+                         void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
  * Forward only with pulses shared per target (trainer.py:113-120 evaluate;

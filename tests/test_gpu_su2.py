@@ -100,14 +100,14 @@ def test_grape_L256(dtype, fast):
 
 
 # ----------------------------------------------------------------------------- all launch shapes
-# (samples/thread, lanes/sample, scalar-instead-of-packed-f32x2)
-SHAPES = [(1, 1, False), (2, 1, False), (4, 1, False), (2, 1, True), (4, 1, True), (1, 2, False), (1, 4, False),
-          (1, 8, False), (1, 16, False), (1, 32, False)]
+# (samples/thread, lanes/sample, scalar-instead-of-packed-f32x2, warps per sample group of the packed kernel)
+SHAPES = [(1, 1, False, 0), (2, 1, False, 1), (4, 1, False, 1), (2, 1, True, 0), (4, 1, True, 0), (2, 1, False, 4),
+          (4, 1, False, 4), (1, 2, False, 0), (1, 4, False, 0), (1, 8, False, 0), (1, 16, False, 0), (1, 32, False, 0)]
 
 
-@pytest.mark.parametrize("st,lps,nopk", SHAPES)
+@pytest.mark.parametrize("st,lps,nopk,wps", SHAPES)
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_every_launch_shape_matches_oracle(st, lps, nopk, dtype):
+def test_every_launch_shape_matches_oracle(st, lps, nopk, wps, dtype):
     rng = np.random.default_rng(10 * st + lps)
     B, L, M = 3, 37, 150          # L not a multiple of anything, M not a multiple of the tile
     pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
@@ -117,7 +117,7 @@ def test_every_launch_shape_matches_oracle(st, lps, nopk, dtype):
         pulses, err = pulses.astype(np.float32), err.astype(np.float32)
     want_l, want_g, want_F = orc.loss_and_grad(pulses, T, err, M, "sharp")
     for splits in (0, 1, 3):
-        flags = uq.tuning_flags(st=st, lps=lps, splits=splits, no_packed=nopk)
+        flags = uq.tuning_flags(st=st, lps=lps, splits=splits, no_packed=nopk, wps=wps)
         val, grad, F, _ = _fused(pulses, T, err, M, dtype, flags=flags)
         tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (3e-5, F32_TOL_G)
         assert np.abs(F - want_F).max() < tolF, (st, lps, splits)
@@ -125,8 +125,8 @@ def test_every_launch_shape_matches_oracle(st, lps, nopk, dtype):
         assert abs(val - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
 
 
-@pytest.mark.parametrize("st,lps,nopk", SHAPES)
-def test_forward_only_U_out_every_shape(st, lps, nopk):
+@pytest.mark.parametrize("st,lps,nopk,wps", SHAPES)
+def test_forward_only_U_out_every_shape(st, lps, nopk, wps):
     rng = np.random.default_rng(5)
     B, L, M = 2, 21, 77
     pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.5, 4.0, (B, L))], -1)   # big angles: sign tracking
@@ -143,7 +143,7 @@ def test_forward_only_U_out_every_shape(st, lps, nopk):
         U = torch.empty(B * M, 2, 2, 2, dtype=dtype, device=DEV)
         F = torch.empty(B * M, dtype=dtype, device=DEV)
         ops._launch_forward(p, uq.target_coeffs(_t(T), dtype), _t(err, dtype), M, 0, (1.0, 0.05), 0, 0, U, F, None, None,
-                            uq.tuning_flags(st=st, lps=lps, no_packed=nopk))
+                            uq.tuning_flags(st=st, lps=lps, no_packed=nopk, wps=wps))
         Uc = torch.view_as_complex(U).cpu().numpy()
         assert np.abs(Uc - want_U).max() < tol
         assert np.abs(F.cpu().numpy() - want_F).max() < 5 * tol

@@ -26,6 +26,8 @@ SIGNATURES = {
     "uqoc_su2_workspace_bytes": (_i64, [_i64, _i64, _i64, _int, _uint]),
     "uqoc_su2_fwdbwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
                                _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
+    "uqoc_su2_fwdbwd_loss": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64, _int, _dbl, _dbl,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_su2_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
                                 _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_su2_forward_grid": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),

@@ -7,6 +7,9 @@
 #include "uqoc_su2_kernels.cuh"
 #include "uqoc_su2_x2.cuh"
 
+extern "C" int uqoc_loss_finalize(const void* Fsum, int64_t B, double n_total, int loss_kind, double tau, double k, void* G,
+                                  int64_t G_numel, void* loss_out, int dtype, void* stream);
+
 namespace uqoc {
 
 // ------------------------------------------------------------------ error string
@@ -73,25 +76,37 @@ static Su2Plan make_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fl
     if (flps) lps = flps;
     if (lps > 1) st = 1;
     Su2Plan plan;
+    // few samples, long train: the packed kernel with the pulse train split over the block's 4 warps
+    // (4x the warps for the same samples) beats both ST = 1 and the lane-split scalar kernel
+    int wps = 1;
+    if (dtype == UQOC_F32 && !(flags & UQOC_FLAG_NO_PACKED) && lps == 1 && !fst && N * 2 > one && N < 4 * one && L >= 32) {
+        st = 2;
+        wps = 4;
+    }
+    if (flags & UQOC_FLAG_WPS4) wps = 4;
+    if (flags & UQOC_FLAG_WPS1) wps = 1;
     plan.st = st;
     plan.lps = lps;
+    plan.packed = (dtype == UQOC_F32) && lps == 1 && st >= 2 && !(flags & UQOC_FLAG_NO_PACKED);
+    if (!plan.packed) wps = 1;
+    plan.wps = wps;
     const int nb = (lps == 1) ? 8 : 1;
-    plan.C = round_up((int)((L + lps - 1) / lps), nb);
+    const int chunks = plan.packed ? wps : lps;
+    plan.C = round_up((int)((L + chunks - 1) / chunks), nb);
     if (plan.C < nb) plan.C = nb;
-    const int ts = (kThreads / lps) * st;
+    const int ts = plan.packed ? ((wps == 1 ? kThreads : 32) * st) : (kThreads / lps) * st;
     plan.n_tiles = (int)((M + ts - 1) / ts);
     if (plan.n_tiles < 1) plan.n_tiles = 1;
-    int64_t want = (int64_t)sms * 4;            // ~4 resident blocks per SM
+    int64_t want = (int64_t)sms * (plan.wps == 4 ? 8 : 4);   // resident blocks per SM (light blocks when the train is split)
     int64_t splits = (want + B - 1) / B;
     if (splits > plan.n_tiles) splits = plan.n_tiles;
     if (splits < 1) splits = 1;
     const int fsp = (flags >> 18) & 0xFFF;
     if (fsp) splits = fsp < plan.n_tiles ? fsp : plan.n_tiles;
     plan.splits = (int)splits;
-    plan.packed = (dtype == UQOC_F32) && lps == 1 && st >= 2 && !(flags & UQOC_FLAG_NO_PACKED);
     plan.table = plan.packed && !(flags & UQOC_FLAG_FAST_SINCOS) && !(flags & UQOC_FLAG_NO_TABLE);
     plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd)
-                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, bwd, plan.table) : su2_smem_bytes<float>(lps, plan.C, bwd));
+                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, plan.wps, plan.st, bwd, plan.table) : su2_smem_bytes<float>(lps, plan.C, bwd));
     return plan;
 }
 
@@ -321,11 +336,18 @@ __global__ void pulse_head_kernel(const HeadParams<T> p) {
 }
 
 // ------------------------------------------------------------------ typed entry helpers
+struct LossSpec {
+    double n_total, tau, k;
+    int kind;
+    void* loss_out;
+};
+
 template <typename T>
 static int su2_run(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
                    int64_t M, int64_t j0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* U_out,
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
-                   unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr) {
+                   unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr,
+                   const LossSpec* ls = nullptr) {
     const Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
     Su2Params<T> p;
     p.pulses = (const T*)pulses;
@@ -359,11 +381,19 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     else rc = su2_launch<T, SC_POLY>(p, plan, bwd, stream);
     if (rc != 0) return rc;
     if (plan.splits > 1 && (Fsum != nullptr || n_g > 0)) {
-        const long long n = n_g + (Fsum != nullptr ? B : 0);
-        const unsigned blocks = (unsigned)((n + 31) / 32);
-        su2_reduce_partials<T><<<blocks, 256, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, (T*)Fsum, (T*)G);
-        return launch_status("su2_reduce_partials");
+        if (ls != nullptr && (int64_t)plan.splits * B <= 65536 && Fsum != nullptr) {
+            const long long n = n_g + B;
+            su2_reduce_finalize<T><<<(unsigned)((n + 31) / 32), 1024, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g,
+                                                                                ls->n_total, ls->kind, ls->tau, ls->k, (T*)Fsum,
+                                                                                (T*)G, (T*)ls->loss_out);
+            return launch_status("su2_reduce_finalize");
+        }
+        launch_reduce_partials<T>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, (T*)Fsum, (T*)G, stream);
+        rc = launch_status("su2_reduce_partials");
+        if (rc) return rc;
     }
+    if (ls != nullptr)
+        return uqoc_loss_finalize(Fsum, B, ls->n_total, ls->kind, ls->tau, ls->k, G, n_g, ls->loss_out, dtype, (void*)stream);
     return 0;
 }
 
@@ -429,6 +459,22 @@ int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, c
                                Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream);
     return su2_run<float>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
                           G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream);
+}
+
+int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M,
+                         double sig_d, double sig_e, uint64_t seed, uint64_t offset, int loss_kind, double tau, double k,
+                         void* F_out, void* err_out, void* Fsum, void* G, void* loss_out, void* workspace,
+                         int64_t workspace_bytes, int dtype, unsigned flags, void* stream) {
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && target_c && Fsum && G && loss_out, "pulses, target_c, Fsum, G and loss_out must be non-null");
+    UQOC_CHECK_ARG(loss_kind >= 0 && loss_kind <= 3, "unknown loss kind %d", loss_kind);
+    LossSpec ls{(double)B * (double)M, tau, k, loss_kind, loss_out};
+    if (dtype == UQOC_F64)
+        return su2_run<double>(pulses, target_c, err, nullptr, B, L, M, 0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out,
+                               Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, &ls);
+    return su2_run<float>(pulses, target_c, err, nullptr, B, L, M, 0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
+                          G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, &ls);
 }
 
 int uqoc_su2_forward(const void* pulses, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M, int64_t j0,

@@ -206,13 +206,16 @@ struct SampleConst {
 };
 template <typename T>
 __device__ __forceinline__ SampleConst<T> make_sample_const(T delta, T eps) {
+    // double arithmetic, one rounding each; rsqrt + multiplies only (no double sqrt / divide)
     const double d = (double)delta, e = (double)eps;
-    const double w = ::sqrt(1.0 + d * d);
+    const double x = ::fma(d, d, 1.0);
+    const double r = ::rsqrt(x);          // 1/w, correctly rounded to ~1 ulp in double
+    const double w = x * r;
     SampleConst<T> k;
     k.a = (T)(0.5 * (1.0 + e) * w);
     k.a2 = (T)((1.0 + e) * w);
-    k.r = (T)(1.0 / w);
-    k.r2 = (T)(1.0 / (w * w));
+    k.r = (T)r;
+    k.r2 = (T)(r * r);
     k.delta = delta;
     k.ae = (T)(0.5 * (1.0 + e));
     return k;

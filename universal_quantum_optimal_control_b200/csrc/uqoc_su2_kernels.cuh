@@ -385,31 +385,120 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
 }
 
 // ---- second stage: fixed-order sum of the per-split partials --------------------------------
-// Block = 32 outputs x 8 split-lanes: lane y sums splits y, y+8, ... (coalesced 128 B rows), then a
-// fixed-order combine over y through shared memory.  Fsum rides along as outputs [n_g, n_g + B).
-template <typename T>
-__global__ void __launch_bounds__(256) su2_reduce_partials(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
-                                                           int splits, int B, long long n_g /* B*L*2 or 0 */,
-                                                           T* __restrict__ Fsum, T* __restrict__ G) {
-    __shared__ T red[8][33];
+// Block = 32 outputs x YL split-lanes: lane y sums splits y, y+YL, ... (coalesced 128 B rows, loads
+// independent so they pipeline), then a fixed-order combine over y through shared memory.  Fsum rides
+// along as outputs [n_g, n_g + B).  Deterministic: the summation order depends only on `splits`.
+template <typename T, int YL>
+__global__ void __launch_bounds__(32 * YL) su2_reduce_partials(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
+                                                               int splits, int B, long long n_g /* B*L*P or 0 */,
+                                                               T* __restrict__ Fsum, T* __restrict__ G) {
+    __shared__ T red[YL][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const long long i = (long long)blockIdx.x * 32 + x;
     const long long n_f = (Fsum != nullptr) ? B : 0;
     T tot = (T)0;
     if (i < n_g) {
-        for (int s = y; s < splits; s += 8) tot += G_part[(size_t)s * n_g + i];
+#pragma unroll 8
+        for (int s = y; s < splits; s += YL) tot += G_part[(size_t)s * n_g + i];
     } else if (i < n_g + n_f) {
-        for (int s = y; s < splits; s += 8) tot += Fsum_part[(size_t)s * B + (i - n_g)];
+#pragma unroll 8
+        for (int s = y; s < splits; s += YL) tot += Fsum_part[(size_t)s * B + (i - n_g)];
     }
     red[y][x] = tot;
     __syncthreads();
     if (y == 0) {
         T t = red[0][x];
 #pragma unroll
-        for (int yy = 1; yy < 8; ++yy) t += red[yy][x];
+        for (int yy = 1; yy < YL; ++yy) t += red[yy][x];
         if (i < n_g) G[i] = t;
         else if (i < n_g + n_f) Fsum[i - n_g] = t;
     }
+}
+
+// ---- fused second stage + loss epilogue (single GPU, no exchange step in between) -----------------
+// Every block first recomputes Fbar = sum_{split,b} Fsum_part / n_total with the same fixed-order tree
+// (bit-identical across blocks), evaluates the loss and d loss / d Fbar, then reduces its 32 outputs over
+// the splits and scales them.  Saves one launch per step, which matters at BASELINE config 3 size.
+__device__ __forceinline__ void su2_loss_eval(double Fbar, int kind, double tau, double k, double& val, double& dval) {
+    if (kind == UQOC_LOSS_SHARP) {
+        const double z = exp(-k * (Fbar - tau));
+        const double lg = log(1.0 + z);
+        val = lg * (1.0 - Fbar);
+        dval = -k * z / (1.0 + z) * (1.0 - Fbar) - lg;
+    } else if (kind == UQOC_LOSS_NLL) {
+        val = -log(Fbar);
+        dval = -1.0 / Fbar;
+    } else if (kind == UQOC_LOSS_INFIDELITY) {
+        val = 1.0 - Fbar;
+        dval = -1.0;
+    } else {
+        val = Fbar;
+        dval = 1.0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) su2_reduce_finalize(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
+                                                            int splits, int B, long long n_g, double n_total, int kind,
+                                                            double tau, double k, T* __restrict__ Fsum, T* __restrict__ G,
+                                                            T* __restrict__ loss_out) {
+    constexpr int YL = 32;
+    __shared__ T red[YL][33];
+    __shared__ double fred[1024];
+    __shared__ double s_scale;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    // Fbar: fixed-order strided partial sums + tree
+    {
+        double a = 0.0;
+        const long long nf = (long long)splits * B;
+        for (long long i = threadIdx.x; i < nf; i += 1024) a += (double)Fsum_part[i];
+        fred[threadIdx.x] = a;
+        __syncthreads();
+        for (int d = 512; d >= 1; d >>= 1) {
+            if ((int)threadIdx.x < d) fred[threadIdx.x] += fred[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double val, dval;
+            const double Fbar = fred[0] / n_total;
+            su2_loss_eval(Fbar, kind, tau, k, val, dval);
+            s_scale = dval / n_total;
+            if (blockIdx.x == 0 && loss_out != nullptr) {
+                loss_out[0] = (T)val;
+                loss_out[1] = (T)Fbar;
+                loss_out[2] = (T)dval;
+            }
+        }
+        __syncthreads();
+    }
+    const long long i = (long long)blockIdx.x * 32 + x;
+    const long long n_f = (Fsum != nullptr) ? B : 0;
+    T tot = (T)0;
+    if (i < n_g) {
+#pragma unroll 8
+        for (int s = y; s < splits; s += YL) tot += G_part[(size_t)s * n_g + i];
+    } else if (i < n_g + n_f) {
+#pragma unroll 8
+        for (int s = y; s < splits; s += YL) tot += Fsum_part[(size_t)s * B + (i - n_g)];
+    }
+    red[y][x] = tot;
+    __syncthreads();
+    if (y == 0) {
+        T t = red[0][x];
+#pragma unroll
+        for (int yy = 1; yy < YL; ++yy) t += red[yy][x];
+        if (i < n_g) G[i] = t * (T)s_scale;
+        else if (i < n_g + n_f) Fsum[i - n_g] = t;
+    }
+}
+
+template <typename T>
+inline void launch_reduce_partials(const T* Fsum_part, const T* G_part, int splits, int B, long long n_g, T* Fsum, T* G,
+                                   cudaStream_t stream) {
+    const long long n = n_g + (Fsum != nullptr ? B : 0);
+    const unsigned blocks = (unsigned)((n + 31) / 32);
+    if (splits > 64) su2_reduce_partials<T, 32><<<blocks, 1024, 0, stream>>>(Fsum_part, G_part, splits, B, n_g, Fsum, G);
+    else su2_reduce_partials<T, 8><<<blocks, 256, 0, stream>>>(Fsum_part, G_part, splits, B, n_g, Fsum, G);
 }
 
 // =============================================================================================
@@ -503,6 +592,7 @@ struct Su2Plan {
     int st, lps, splits, n_tiles, C;
     size_t smem;
     bool packed;   // FP32 only: f32x2 (FFMA2) kernel, two samples per register pair
+    int wps;       // packed kernel: warps per sample group (1, or 4 = pulse train split over the block's warps)
     bool table;    // packed kernel: table-lookup sin/cos instead of the polynomial pair
 };
 

@@ -26,9 +26,9 @@ static int su2_launch_one(const Su2Params<T>& p, const Su2Plan& plan, cudaStream
     return launch_status("su2_kernel");
 }
 
-template <int NP, int SC, bool BWD>
-static int su2_launch_x2(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
-    auto kern = su2_kernel_x2<NP, SC, BWD>;
+template <int NP, int SC, bool BWD, int WPS>
+static int su2_launch_x2w(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
+    auto kern = su2_kernel_x2<NP, SC, BWD, WPS>;
     if (plan.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) {
@@ -40,6 +40,11 @@ static int su2_launch_x2(const Su2Params<float>& p, const Su2Plan& plan, cudaStr
     const unsigned grid = (unsigned)((long long)p.B * plan.splits);
     kern<<<grid, kThreads, plan.smem, stream>>>(p);
     return launch_status("su2_kernel_x2");
+}
+template <int NP, int SC, bool BWD>
+static int su2_launch_x2(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
+    if (plan.wps == 4) return su2_launch_x2w<NP, SC, BWD, 4>(p, plan, stream);
+    return su2_launch_x2w<NP, SC, BWD, 1>(p, plan, stream);
 }
 
 template <typename T, int SC, bool BWD>

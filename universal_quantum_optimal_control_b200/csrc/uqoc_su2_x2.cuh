@@ -178,36 +178,45 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
     }
 }
 
-// shared memory of one block of the packed kernel (bytes)
-__host__ __device__ inline size_t su2_x2_smem_bytes(int C, bool bwd, bool table) {
-    size_t bytes = (size_t)C * 16 + (size_t)C * 8;               // {c,c,s,s} rows + {tau,tau}
-    if (table) bytes += 2 * (size_t)UQOC_SINCOS_TABLE_N * sizeof(float);
-    if (bwd) bytes += (size_t)C * 16;                            // {cd,cd,sd,sd} rows
-    if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);    // per-warp gradient accumulators
+// shared memory of one block of the packed kernel (bytes).  C = pulses per chunk, WPS chunks.
+__host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool bwd, bool table) {
+    const size_t rows = (size_t)C * wps;
+    size_t bytes = rows * 16 + rows * 8;                          // {c,c,s,s} rows + {tau,tau}
+    if (bwd) bytes += rows * 16;                                  // {cd,cd,sd,sd} rows
+    if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);     // gradient accumulators (per warp / per chunk)
     bytes += 32 * sizeof(float);
+    if (table) bytes += 2 * (size_t)UQOC_SINCOS_TABLE_N * sizeof(float);
+    if (wps > 1) bytes += (size_t)kWarps * st * 5 * 32 * sizeof(float);   // chunk-product (+ parity) exchange
     return bytes;
 }
 
-// NP = sample PAIRS per thread (1 or 2)
 // resident-block hint: the table kernel has LDS latency to hide, 6 blocks/SM (<= 80 registers) measured best
-constexpr int x2_min_blocks(int NP, int SC) { return (SC == SC_TABLE) ? 6 : 1; }
+constexpr int x2_min_blocks(int NP, int SC, int WPS) { return (WPS == 4 && NP == 1) ? 7 : ((SC == SC_TABLE) ? 6 : 1); }
 
-template <int NP, int SC, bool BWD>
-__global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2(const Su2Params<float> p) {
+// NP  = sample PAIRS per thread (1 or 2)
+// WPS = warps per sample group.  1: every warp owns its own 32*ST samples and the whole pulse train.
+//       4: the block's four warps share 32*ST samples and each owns a quarter of the pulse train
+//       (chunk products exchanged through shared memory; the prefix alone seeds every chunk's backward
+//       sweep, see uqoc_su2_kernels.cuh) -- 4x the warps for the same samples, for small sample counts.
+template <int NP, int SC, bool BWD, int WPS>
+__global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kernel_x2(const Su2Params<float> p) {
     constexpr int ST = 2 * NP;
     constexpr int NB = 8;
-    constexpr int TS = kThreads * ST;
+    constexpr int SLOTS = (WPS == 1) ? kThreads : 32;     // sample slots per block
+    constexpr int TS = SLOTS * ST;
     constexpr int NV = 2 * NB;
 
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int C = p.C;
+    const int C = p.C;                 // pulses per chunk (multiple of NB)
+    const int CT = C * WPS;            // staged rows
     float4* fwd4 = reinterpret_cast<float4*>(smem_raw);
-    float4* bwd4 = fwd4 + C;
-    float2* tau2 = reinterpret_cast<float2*>(bwd4 + (BWD ? C : 0));
-    float* acc = reinterpret_cast<float*>(tau2 + C);
+    float4* bwd4 = fwd4 + CT;
+    float2* tau2 = reinterpret_cast<float2*>(bwd4 + (BWD ? CT : 0));
+    float* acc = reinterpret_cast<float*>(tau2 + CT);
     float* scratch = acc + (BWD ? (size_t)kWarps * C * 2 : 0);
     float* tsin = scratch + 32;
     float* tcos = tsin + kTabN;
+    float* xq = tcos + (SC == SC_TABLE ? kTabN : -kTabN);   // [kWarps][ST][5][32], WPS > 1 only
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -215,10 +224,13 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
     const int split = blockIdx.x % p.splits;
     const int b = blockIdx.x / p.splits;
     const int L = p.L;
+    const int rb = (WPS == 1) ? 0 : warp * C;              // first staged row of this warp's chunk
+    const int slot = (WPS == 1) ? tid : lane;
+    const bool lead = (WPS == 1) || warp == 0;             // the warp that reports per-sample outputs
 
     {
         const float* pb = p.pulses + (size_t)b * L * 2;
-        for (int i = tid; i < C; i += kThreads) {
+        for (int i = tid; i < CT; i += kThreads) {
             const int ic = i < L ? i : L - 1;
             const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
             const double phi = (double)pb[2 * ic];
@@ -264,13 +276,13 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
             SampleConst<float> kc[ST];
 #pragma unroll
             for (int u = 0; u < ST; ++u) {
-                const long long j = (long long)tile * TS + u * kThreads + tid;
+                const long long j = (long long)tile * TS + u * SLOTS + slot;
                 valid[u] = j < p.M;
                 sidx[u] = (size_t)b * p.M + (size_t)(valid[u] ? j : 0);
                 float delta = 0.0f, eps = 0.0f;
                 if (valid[u]) {
                     su2_sample_errors<float>(p, b, j, sidx[u], Bm, delta, eps);
-                    if (p.err_out != nullptr) {
+                    if (p.err_out != nullptr && lead) {
                         p.err_out[sidx[u]] = delta;
                         p.err_out[Bm + sidx[u]] = eps;
                     }
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
             }
         }
 
-        // ---------------- forward sweep ----------------
+        // ---------------- forward sweep over this warp's chunk ----------------
         F2 Pa[NP], Pb[NP], Pc[NP], Pd[NP];
         int par[ST];
 #pragma unroll
@@ -298,8 +310,8 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
         }
 #pragma unroll 2
         for (int jj = 0; jj < C; ++jj) {
-            const float4 row = fwd4[jj];
-            const float2 tt = tau2[jj];
+            const float4 row = fwd4[rb + jj];
+            const float2 tt = tau2[rb + jj];
             const F2 cc = f2(row.x, row.y), ss = f2(row.z, row.w), tau = f2(tt.x, tt.y);
             F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP], na[NP], nb[NP], nc[NP], nd[NP];
             int kb[ST];
@@ -341,14 +353,48 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
             for (int u = 0; u < NP; ++u) { Pa[u] = na[u]; Pb[u] = nb[u]; Pc[u] = nc[u]; Pd[u] = nd[u]; }
         }
 
-        // ---------------- fidelity epilogue (scalar, once per sample) ----------------
-        Quat<float> PL[ST];
-        float trr[ST], tri[ST];
+        // ---------------- chunk products -> prefix at this chunk's end and the full product ----------------
+        Quat<float> PL[ST], Pin[ST];
 #pragma unroll
         for (int u = 0; u < ST; ++u) {
             const int pu = u >> 1;
-            Quat<float> q = (u & 1) ? Quat<float>{f2hi(Pa[pu]), f2hi(Pb[pu]), f2hi(Pc[pu]), f2hi(Pd[pu])}
-                                    : Quat<float>{f2lo(Pa[pu]), f2lo(Pb[pu]), f2lo(Pc[pu]), f2lo(Pd[pu])};
+            Pin[u] = (u & 1) ? Quat<float>{f2hi(Pa[pu]), f2hi(Pb[pu]), f2hi(Pc[pu]), f2hi(Pd[pu])}
+                             : Quat<float>{f2lo(Pa[pu]), f2lo(Pb[pu]), f2lo(Pc[pu]), f2lo(Pd[pu])};
+            PL[u] = Pin[u];
+        }
+        if constexpr (WPS > 1) {
+#pragma unroll
+            for (int u = 0; u < ST; ++u) {
+                float* dst = xq + ((size_t)(warp * ST + u) * 5) * 32 + lane;
+                dst[0] = Pin[u].a; dst[32] = Pin[u].b; dst[64] = Pin[u].c; dst[96] = Pin[u].d;
+                dst[128] = __int_as_float(par[u] & 1);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < ST; ++u) {
+                const float* s0 = xq + ((size_t)u * 5) * 32 + lane;
+                Quat<float> run{s0[0], s0[32], s0[64], s0[96]};
+                int ptot = __float_as_int(s0[128]);
+                if (warp == 0) Pin[u] = run;
+#pragma unroll
+                for (int w2 = 1; w2 < WPS; ++w2) {
+                    const float* sw = xq + ((size_t)(w2 * ST + u) * 5) * 32 + lane;
+                    const Quat<float> Qw{sw[0], sw[32], sw[64], sw[96]};
+                    ptot ^= __float_as_int(sw[128]);
+                    run = qmul(Qw, run);                   // later pulses on the left
+                    if (w2 == warp) Pin[u] = run;
+                }
+                PL[u] = run;
+                par[u] = ptot;                             // parity of the whole train (U_out sign)
+            }
+            __syncthreads();                               // xq is rewritten by the next tile
+        }
+
+        // ---------------- fidelity epilogue (scalar, once per sample) ----------------
+        float trr[ST], tri[ST];
+#pragma unroll
+        for (int u = 0; u < ST; ++u) {
+            Quat<float> q = PL[u];
             const float n2 = q.a * q.a + q.b * q.b + q.c * q.c + q.d * q.d;
             const float inv = 1.0f / sqrtf(n2);
             q.a *= inv; q.b *= inv; q.c *= inv; q.d *= inv;
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
             trr[u] = cr[0] * q.a + cr[1] * q.b + cr[2] * q.c + cr[3] * q.d;
             tri[u] = ci[0] * q.a + ci[1] * q.b + ci[2] * q.c + ci[3] * q.d;
             const float F = (trr[u] * trr[u] + tri[u] * tri[u] + 2.0f) * (1.0f / 6.0f);
-            if (valid[u]) {
+            if (valid[u] && lead) {
                 fsum += F;
                 if (p.F_out != nullptr) p.F_out[sidx[u]] = F;
                 if (!BWD && p.U_out != nullptr) {
@@ -371,10 +417,10 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
         }
 
         if constexpr (BWD) {
-            // ---------------- adjoint seed ----------------
+            // ---------------- adjoint seed at the end of this warp's chunk ----------------
             F2 A[NP], Bq[NP], W3[NP];
             {
-                const float4 rowL = fwd4[C - 1];
+                const float4 rowL = fwd4[rb + C - 1];
                 float a_[ST], b_[ST], w_[ST];
 #pragma unroll
                 for (int u = 0; u < ST; ++u) {
@@ -383,7 +429,13 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
                     const float fr = wgt * trr[u] * (1.0f / 3.0f), fi = wgt * tri[u] * (1.0f / 3.0f);
                     const Quat<float> lam{fr * cr[0] + fi * ci[0], fr * cr[1] + fi * ci[1], fr * cr[2] + fi * ci[2],
                                           fr * cr[3] + fi * ci[3]};
-                    const Quat<float> Wq = qmul(lam, qconj(PL[u]));
+                    Quat<float> Wq;
+                    if constexpr (WPS > 1) {
+                        const Quat<float> Lam = qmul(qconj(PL[u]), lam);
+                        Wq = qmul(qmul(Pin[u], Lam), qconj(Pin[u]));
+                    } else {
+                        Wq = qmul(lam, qconj(PL[u]));
+                    }
                     a_[u] = Wq.b * rowL.x + Wq.c * rowL.z;
                     b_[u] = Wq.c * rowL.x - Wq.b * rowL.z;
                     w_[u] = Wq.d;
@@ -401,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
                 float v[NV];
 #pragma unroll
                 for (int e = NB - 1; e >= 0; --e) {
-                    const float4 row = bwd4[jb * NB + e];
-                    const float2 tt = tau2[jb * NB + e];
+                    const float4 row = bwd4[rb + jb * NB + e];
+                    const float2 tt = tau2[rb + jb * NB + e];
                     const F2 cd = f2(row.x, row.y), sd = f2(row.z, row.w), tau = f2(tt.x, tt.y);
                     F2 gp = f2b(0.0f), gt = f2b(0.0f);
                     F2 h[NP], s[NP], c[NP], s2[NP], C2[NP], Sr[NP], k1_[NP], t[NP], uu[NP], K[NP], BS[NP], A1[NP], B1[NP], Wz[NP];
@@ -456,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
                 constexpr int NF = reduce_final_count(NV, 1);
                 constexpr int DUP = reduce_dup_mask(NV, 1);
                 if ((lane & DUP) == 0) {
+                    // WPS = 1: per-warp slice of the whole train;  WPS = 4: this warp's chunk of the train
                     float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
 #pragma unroll
                     for (int m = 0; m < NF; ++m) dst[m] += v[m];
@@ -480,9 +533,14 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC)) su2_kernel_x2
         float* gout = p.G_part + ((size_t)split * p.B + b) * L * 2;
         const int LC2 = C * 2;
         for (int i = tid; i < 2 * L; i += kThreads) {
-            float tot = 0.0f;
+            float tot;
+            if constexpr (WPS == 1) {
+                tot = 0.0f;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
+                for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
+            } else {
+                tot = acc[i];                              // chunks are consecutive: flat index == pulse index
+            }
             gout[i] = (i & 1) ? tot : tot * 0.5f;
         }
     }

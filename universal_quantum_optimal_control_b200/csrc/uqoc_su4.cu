@@ -435,8 +435,7 @@ static int su4_run(const void* pulses, const void* target, const void* err, cons
     int rc = launch_status("su4_kernel");
     if (rc) return rc;
     if (pl.splits > 1 && (Fsum != nullptr || n_g > 0)) {
-        const long long n = n_g + (Fsum != nullptr ? B : 0);
-        su2_reduce_partials<T><<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(p.Fsum_part, p.G_part, pl.splits, (int)B, n_g, (T*)Fsum, (T*)G);
+        launch_reduce_partials<T>(p.Fsum_part, p.G_part, pl.splits, (int)B, n_g, (T*)Fsum, (T*)G, stream);
         return launch_status("su4 reduce_partials");
     }
     return 0;

@@ -58,10 +58,8 @@ class GraphedFusedStep:
         self.d_rng.copy_(self.h_rng, non_blocking=True)
         tc = ops.target_coeffs(self.d_target, self.d_pulses.dtype)
         Fsum, G = self.d_out[3:3 + B], self.d_out[3 + B:]
-        ops._launch_fwdbwd(self.d_pulses, tc, self.d_err, None, M, 0, self.sigma, self.d_rng.data_ptr(), 0, None, None, Fsum, G,
-                           self.flags | FLAG_RNG_FROM_DEVICE)
-        lo = ops._finalize(Fsum, B * M, self.loss, self.tau, self.k, G)
-        self.d_out[:3].copy_(lo)
+        ops._launch_fwdbwd_loss(self.d_pulses, tc, self.d_err, M, self.sigma, self.d_rng.data_ptr(), 0, self.loss, self.tau, self.k,
+                                None, None, Fsum, G, self.d_out[:3], self.flags | FLAG_RNG_FROM_DEVICE)
         self.h_out.copy_(self.d_out, non_blocking=True)
 
     def capture(self):

@@ -74,9 +74,10 @@ def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:
 
 
 def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool = False, no_packed: bool = False,
-                 no_table: bool = False) -> int:
+                 no_table: bool = False, wps: int = 0) -> int:
     """Pack the launch-shape overrides of include/uqoc.h (0 = library heuristic)."""
-    return ((FLAG_FAST_SINCOS if fast_sincos else 0) | (2 if no_packed else 0) | (4 if no_table else 0) | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
+    return ((FLAG_FAST_SINCOS if fast_sincos else 0) | (2 if no_packed else 0) | (4 if no_table else 0)
+            | (16 if wps == 4 else 0) | (32 if wps == 1 else 0) | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
             | ((splits & 0xFFF) << 18))
 
 
@@ -122,6 +123,18 @@ def _launch_fwdbwd(pulses, tc, error, weight, M, j0, sigma, seed, offset, F_out,
                               ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su2_fwdbwd")
 
 
+def _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags):
+    """Single-GPU step: fused kernel + (fused) partials reduction + loss epilogue, <= 2 launches."""
+    B, L, _ = pulses.shape
+    lib = _lib.lib()
+    dt = _dt(pulses)
+    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
+    ws = _workspace(ws_bytes, pulses.device)
+    check(lib.uqoc_su2_fwdbwd_loss(_ptr(pulses), _ptr(tc), _ptr(error), B, L, M, float(sigma[0]), float(sigma[1]), seed, offset,
+                                   LOSS_KINDS[loss], float(tau), float(k), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G),
+                                   _ptr(loss_out), _ptr(ws), ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su2_fwdbwd_loss")
+
+
 def _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, U_out, F_out, err_out, Fsum, flags):
     B, L, _ = pulses.shape
     lib = _lib.lib()
@@ -148,14 +161,18 @@ class _FusedPropagateLoss(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         buf = torch.empty(B + (B * L * 2 if need_grad else 0), dtype=pulses.dtype, device=pulses.device)
         Fsum, G = buf[:B], (buf[B:] if need_grad else None)
-        if need_grad:
-            _launch_fwdbwd(pulses, tc, error, None, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags)
+        if need_grad and group is None:
+            loss_out = torch.empty(3, dtype=pulses.dtype, device=pulses.device)
+            _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags)
         else:
-            _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, None, F_out, err_out, Fsum, flags)
-        if group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)   # [Fsum | G]: the one exchange step
-        loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
+            if need_grad:
+                _launch_fwdbwd(pulses, tc, error, None, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags)
+            else:
+                _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, None, F_out, err_out, Fsum, flags)
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)   # [Fsum | G]: the one exchange step
+            loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
         mean_fid = Fsum / M_total
         if need_grad:
             ctx.save_for_backward(G.view(B, L, 2))
