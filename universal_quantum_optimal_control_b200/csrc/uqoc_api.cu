@@ -27,11 +27,17 @@ int su2_launch(const Su2Params<T>& p, const Su2Plan& plan, bool bwd, cudaStream_
 template <> int su2_launch<float, SC_POLY>(const Su2Params<float>&, const Su2Plan&, bool, cudaStream_t);
 template <> int su2_launch<float, SC_MUFU>(const Su2Params<float>&, const Su2Plan&, bool, cudaStream_t);
 template <> int su2_launch<double, SC_LIBM>(const Su2Params<double>&, const Su2Plan&, bool, cudaStream_t);
+template <> int su2_launch<double, SC_TABLE>(const Su2Params<double>&, const Su2Plan&, bool, cudaStream_t);
 
 // su2_launch<float, SC_LIBM> / <double, SC_POLY|SC_MUFU> are never instantiated: route by type.
 template <>
 int su2_launch<float, SC_LIBM>(const Su2Params<float>&, const Su2Plan&, bool, cudaStream_t) {
     set_error("internal: float/libm path not built");
+    return UQOC_E_UNSUPPORTED;
+}
+template <>
+int su2_launch<float, SC_TABLE>(const Su2Params<float>&, const Su2Plan&, bool, cudaStream_t) {
+    set_error("internal: float/table scalar path not built");
     return UQOC_E_UNSUPPORTED;
 }
 template <>
@@ -105,7 +111,7 @@ static Su2Plan make_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fl
     if (fsp) splits = fsp < plan.n_tiles ? fsp : plan.n_tiles;
     plan.splits = (int)splits;
     plan.table = plan.packed && !(flags & UQOC_FLAG_FAST_SINCOS) && !(flags & UQOC_FLAG_NO_TABLE);
-    plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd)
+    plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd, (flags & UQOC_FLAG_NO_TABLE) ? 0 : 1024)
                                     : (plan.packed ? su2_x2_smem_bytes(plan.C, plan.wps, plan.st, bwd, plan.table) : su2_smem_bytes<float>(lps, plan.C, bwd));
     return plan;
 }
@@ -376,7 +382,7 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
         p.G_part = (T*)G;
     }
     int rc;
-    if (dtype == UQOC_F64) rc = su2_launch<T, SC_LIBM>(p, plan, bwd, stream);
+    if (dtype == UQOC_F64) rc = (flags & UQOC_FLAG_NO_TABLE) ? su2_launch<T, SC_LIBM>(p, plan, bwd, stream) : su2_launch<T, SC_TABLE>(p, plan, bwd, stream);
     else if (flags & UQOC_FLAG_FAST_SINCOS) rc = su2_launch<T, SC_MUFU>(p, plan, bwd, stream);
     else rc = su2_launch<T, SC_POLY>(p, plan, bwd, stream);
     if (rc != 0) return rc;

@@ -63,18 +63,22 @@ __device__ __forceinline__ void sincos_modpi(float h, float& s, float& c, int& k
 
 template <typename T, int SC>
 struct SinCos;
+// every policy exposes eval(h, s, c, kbits, tab): `tab` is the shared-memory table {sin[N] | cos[N]} of the
+// policies with kTableN > 0 and is ignored by the others.
 
 template <>
 struct SinCos<float, SC_POLY> {
     static constexpr bool kTracksParity = true;
-    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits) {
+    static constexpr int kTableN = 0;
+    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits, const float* = nullptr) {
         sincos_modpi(h, s, c, kbits);
     }
 };
 template <>
 struct SinCos<float, SC_MUFU> {
     static constexpr bool kTracksParity = false;
-    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits) {
+    static constexpr int kTableN = 0;
+    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits, const float* = nullptr) {
         kbits = 0;
         __sincosf(h, &s, &c);
     }
@@ -82,17 +86,44 @@ struct SinCos<float, SC_MUFU> {
 template <>
 struct SinCos<float, SC_LIBM> {
     static constexpr bool kTracksParity = false;
-    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits) {
+    static constexpr int kTableN = 0;
+    __device__ __forceinline__ static void eval(float h, float& s, float& c, int& kbits, const float* = nullptr) {
         kbits = 0;
         sincosf(h, &s, &c);
     }
 };
-template <int SC>
-struct SinCos<double, SC> {
+template <>
+struct SinCos<double, SC_LIBM> {
     static constexpr bool kTracksParity = false;
-    __device__ __forceinline__ static void eval(double h, double& s, double& c, int& kbits) {
+    static constexpr int kTableN = 0;
+    __device__ __forceinline__ static void eval(double h, double& s, double& c, int& kbits, const double* = nullptr) {
         kbits = 0;
         sincos(h, &s, &c);
+    }
+};
+// FP64 table policy: h = k pi/1024 + r (three-term Cody-Waite, exact for |k| < 2^20), (sin, cos)(k pi/1024) from a
+// double table in shared memory, residual rotation to full double accuracy (sin r to r^5, cos r to r^4:
+// truncation 4e-24 / 2e-20 at |r| <= pi/2048).  15 DFMA-pipe instructions instead of libm's ~45; like the
+// FP32 paths the sign (-1)^(k div 1024) is dropped (kbits = k >> 10 lets the U_out kernel track it).
+template <>
+struct SinCos<double, SC_TABLE> {
+    static constexpr bool kTracksParity = true;
+    static constexpr int kTableN = 1024;
+    __device__ __forceinline__ static void eval(double h, double& s, double& c, int& kbits, const double* tab) {
+        const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+        double kf = ::fma(h, 325.94932345220167, MAGIC);
+        const int k = __double2loint(kf);
+        kbits = k >> 10;
+        kf -= MAGIC;
+        double r = ::fma(kf, -0.003067961575652589, h);
+        r = ::fma(kf, -1.1869336926769907e-13, r);
+        r = ::fma(kf, -6.878046611685938e-30, r);
+        const double st = tab[k & 1023], ct = tab[1024 + (k & 1023)];
+        const double z = r * r;
+        const double sr = ::fma(r * z, ::fma(z, 8.3333333333333332e-03, -1.6666666666666666e-01), r);
+        const double cr = ::fma(z, ::fma(z, 4.1666666666666664e-02, -0.5), 1.0);
+        s = ::fma(ct, sr, st * cr);
+        c = ::fma(-st, sr, ct * cr);
     }
 };
 

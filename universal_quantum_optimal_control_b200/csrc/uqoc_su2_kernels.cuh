@@ -17,6 +17,8 @@
 
 namespace uqoc {
 
+#include "uqoc_sincos_table.inc"
+
 constexpr int kThreads = 128;  // 4 warps: one per SM sub-partition
 constexpr int kWarps = kThreads / 32;
 
@@ -118,9 +120,10 @@ __device__ __forceinline__ Quat<T> qshfl(const Quat<T>& q, int src, int width) {
 
 // shared-memory footprint (bytes) of one block
 template <typename T>
-__host__ __device__ inline size_t su2_smem_bytes(int LPS, int C, bool bwd) {
+__host__ __device__ inline size_t su2_smem_bytes(int LPS, int C, bool bwd, int table_n = 0) {
     const size_t rows = (size_t)LPS * (C + 1);
     size_t bytes = rows * sizeof(Row4<T>);                             // forward table
+    bytes += 2 * (size_t)table_n * sizeof(T);                          // sin/cos table of the table policies
     if (bwd) bytes += rows * sizeof(Row4<T>);                          // backward table
     if (bwd) bytes += (size_t)kWarps * LPS * C * 2 * sizeof(T);        // per-warp gradient accumulators
     bytes += 32 * sizeof(T);                                           // block-reduction scratch
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
     Row4<T>* bwd_tab = fwd_tab + (BWD ? rows : 0);
     T* acc = reinterpret_cast<T*>(bwd_tab + rows);       // [kWarps][LPS*C][2] (BWD only)
     T* scratch = acc + (BWD ? (size_t)kWarps * LPS * C * 2 : 0);
+    T* sctab = scratch + 32;                             // {sin[N] | cos[N]} of the table sin/cos policies
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -174,6 +178,12 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
         }
         if (BWD) {
             for (int i = tid; i < kWarps * LPS * C * 2; i += kThreads) acc[i] = (T)0;
+        }
+        if constexpr (SCP::kTableN > 0) {
+            for (int i = tid; i < SCP::kTableN; i += kThreads) {
+                sctab[i] = (T)g_sin_table_f64[i];
+                sctab[SCP::kTableN + i] = (T)g_cos_table_f64[i];
+            }
         }
     }
     __syncthreads();
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
                 const T h = row.z * kc[u].a;
                 T s, c;
                 int kb;
-                SCP::eval(h, s, c, kb);
+                SCP::eval(h, s, c, kb, sctab);
                 if (SCP::kTracksParity && !BWD) parity[u] ^= kb;
                 const T sp = s * kc[u].r;
                 const T q1 = sp * row.x, q2 = sp * row.y, q3 = sp * kc[u].delta;
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
                         const T h = row.z * kc[u].a;
                         T s, c;
                         int kb;
-                        SCP::eval(h, s, c, kb);
+                        SCP::eval(h, s, c, kb, sctab);
                         const T s2 = s + s;
                         const T C2 = R::fma(-s2, s, (T)1);        // cos 2h
                         const T Sr = (s2 * kc[u].r) * c;          // sin 2h / w

@@ -11,7 +11,6 @@
 
 namespace uqoc {
 
-#include "uqoc_sincos_table.inc"
 constexpr int kTabN = UQOC_SINCOS_TABLE_N;
 
 typedef unsigned long long u64;
