@@ -363,7 +363,7 @@ def main():
             "config": {"workload": ("BASELINE config 5 slice (curriculum, Philox eps on-chip)" if args.workload == "curriculum"
                                     else "BASELINE config 3 (GRAPE, explicit eps)"),
                        "targets_B": B, "pulses_L": L, "samples_per_target_per_gpu": M, "samples_per_target_total": M_total,
-                       "props_per_step": props_step, "loss": "sharp", "sincos": "mufu" if args.fast_sincos else "poly",
+                       "props_per_step": props_step, "loss": "sharp", "sincos": "mufu" if args.fast_sincos else ("poly" if (args.flags & 4) else "table"),
                        "sharding": f"samples x{world}", "l2_flush_between_steps": True,
                        "timing": "CUDA events per step on the launching stream, max over ranks"},
             "e2e": {"value": props_step / (min(e2e_ms, e2e_graph_ms or e2e_ms) * 1e-3), "unit": "prop/s", "h2d_bytes_per_step": h2d,
@@ -373,7 +373,11 @@ def main():
                     "timing": "host wall clock around K steps, pinned host buffers in, pinned host buffers out"},
             "gpu_launches": args.steps * (2 if world == 1 else 2 + (1 if ops._lib.lib().uqoc_su2_workspace_bytes(B, L, M, 0, flags) > 0 else 0)),
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s", "frac": ach_tflops / peak,
-                         "traffic": None, "kernel": "su2_kernel (fused fwd+bwd)", "kernel_ms": kern_ms,
+                         "traffic": ncu_dram_traffic(args.workload) if (rdt == torch.float32 and not args.flags and not args.fast_sincos) else None,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_su2_fwdbwd_bench_launch_ncu.txt)",
+                         "algorithmic_bytes_per_launch": float(B * L * 2 * 4 * 2 + B * 8 * 4 + B * 4),
+                         "kernel": "su2_kernel_x2 (fused fwd+bwd, packed f32x2, table sin/cos)" if rdt == torch.float32 else "su2_kernel<double> (fused fwd+bwd)",
+                         "kernel_ms": kern_ms,
                          "flop_per_prop": FLOP_PER_PROP_FWDBWD,
                          "peak_source": f"nominal FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure)",
                          "measured_ffma_tflops": peak_meas, "measured_ffma2_tflops": peak2},
@@ -390,6 +394,23 @@ def main():
     if group is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_dram_traffic(workload: str):
+    """dram__bytes_read + dram__bytes_write of the fused kernel for THIS launch shape, from the committed
+    `ncu --set full` capture of `tools/profile_fwdbwd.py 4096 4096 256` (profiles/r1_su2_fwdbwd_bench_launch_ncu.txt)."""
+    if workload != "curriculum":
+        return None
+    path = os.path.join(ROOT, "profiles", "r1_su2_fwdbwd_bench_launch_ncu.txt")
+    try:
+        tot, units = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * units.get(f[2], 1.0)
+        return tot
+    except OSError:
+        return None
 
 
 def other_configs(uq, ops, dev):
