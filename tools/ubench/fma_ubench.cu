@@ -24,6 +24,8 @@ template <int MODE> __global__ void __launch_bounds__(256) k_ffma2(int iters, u6
                 if (MODE == 2) a[i] = ffma2(a[i], b[i], c[i]);
                 if (MODE == 3) a[i] = ffma2(b[i], c[(i + 1) % N], a[i]);
                 if (MODE == 4) a[i] = fmul2(a[i], b[i]);
+                if (MODE == 5) { unsigned lo = (unsigned)b[i]; u64 bb; asm volatile("mov.b64 %0, {%1, %1};" : "=l"(bb) : "r"(lo)); a[i] = ffma2(a[i], bb, c[i]); }
+                if (MODE == 6) { unsigned lo = (unsigned)b[i]; u64 bb; asm volatile("mov.b64 %0, {%1, %1};" : "=l"(bb) : "r"(lo)); a[i] = ffma2(a[i], bb, y); }
             }
         }
     }
@@ -66,7 +68,7 @@ int main() {
         float t;
 #define RUN2(M) t = timeit([&] { k_ffma2<M><<<blocks, threads>>>(iters, 3, (u64*)out); }); printf("FFMA2 mode%d warps/SM=%2d: %.2f TFLOP/s\n", M, wpb * 8, flops2 / t / 1e9);
 #define RUN1(M) t = timeit([&] { k_ffma<M><<<blocks, threads>>>(iters, 3.f, (float*)out); }); printf("FFMA  mode%d warps/SM=%2d: %.2f TFLOP/s\n", M, wpb * 8, flops1 / t / 1e9);
-        RUN2(0) RUN2(1) RUN2(2) RUN2(3)
+        RUN2(0) RUN2(1) RUN2(2) RUN2(3) RUN2(5) RUN2(6)
         t = timeit([&] { k_ffma2<4><<<blocks, threads>>>(iters, 3, (u64*)out); }); printf("FMUL2       warps/SM=%2d: %.2f Tmul-lanes x2/s (as FLOP: %.2f)\n", wpb * 8, flops2 / t / 1e9, flops2 / t / 2e9);
         RUN1(0) RUN1(1) RUN1(2) RUN1(3)
     }

@@ -180,8 +180,8 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
 // shared memory of one block of the packed kernel (bytes).  C = pulses per chunk, WPS chunks.
 __host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool bwd, bool table) {
     const size_t rows = (size_t)C * wps;
-    size_t bytes = rows * 16 + rows * 8;                          // {c,c,s,s} rows + {tau,tau}
-    if (bwd) bytes += rows * 16;                                  // {cd,cd,sd,sd} rows
+    size_t bytes = rows * 16;                                     // {cos phi, sin phi, tau, -} rows
+    if (bwd) bytes += rows * 16;                                  // {cos dphi, sin dphi, tau, -} rows
     if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);     // gradient accumulators (per warp / per chunk)
     bytes += 32 * sizeof(float);
     if (table) bytes += 2 * (size_t)UQOC_SINCOS_TABLE_N * sizeof(float);
@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     const int CT = C * WPS;            // staged rows
     float4* fwd4 = reinterpret_cast<float4*>(smem_raw);
     float4* bwd4 = fwd4 + CT;
-    float2* tau2 = reinterpret_cast<float2*>(bwd4 + (BWD ? CT : 0));
-    float* acc = reinterpret_cast<float*>(tau2 + CT);
+    float* acc = reinterpret_cast<float*>(bwd4 + (BWD ? CT : 0));
     float* scratch = acc + (BWD ? (size_t)kWarps * C * 2 : 0);
     float* tsin = scratch + 32;
     float* tcos = tsin + kTabN;
@@ -237,12 +236,11 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             const float tau = i < L ? pb[2 * ic + 1] : 0.0f;
             double sn, cs;
             ::sincos(phi, &sn, &cs);
-            fwd4[i] = make_float4((float)cs, (float)cs, (float)sn, (float)sn);
-            tau2[i] = make_float2(tau, tau);
+            fwd4[i] = make_float4((float)cs, (float)sn, tau, 0.0f);
             if (BWD) {
                 double sd, cd;
                 ::sincos(i == 0 ? 0.0 : phi - phim, &sd, &cd);
-                bwd4[i] = make_float4((float)cd, (float)cd, (float)sd, (float)sd);
+                bwd4[i] = make_float4((float)cd, (float)sd, tau, 0.0f);
             }
         }
         if (BWD) {
@@ -309,9 +307,10 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
         }
 #pragma unroll 2
         for (int jj = 0; jj < C; ++jj) {
+            // per-pulse values are warp-uniform: f2b() lets ptxas use the 32-bit broadcast operand form (R.F32),
+            // which costs no 64-bit register-file read (tools/ubench/fma_ubench.cu modes 5/6)
             const float4 row = fwd4[rb + jj];
-            const float2 tt = tau2[rb + jj];
-            const F2 cc = f2(row.x, row.y), ss = f2(row.z, row.w), tau = f2(tt.x, tt.y);
+            const F2 cc = f2b(row.x), ss = f2b(row.y), tau = f2b(row.z);
             F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP], na[NP], nb[NP], nc[NP], nd[NP];
             int kb[ST];
 #pragma unroll
@@ -419,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             // ---------------- adjoint seed at the end of this warp's chunk ----------------
             F2 A[NP], Bq[NP], W3[NP];
             {
-                const float4 rowL = fwd4[rb + C - 1];
+                const float4 rowL = fwd4[rb + C - 1];      // (cos phi, sin phi) of the chunk's last pulse
                 float a_[ST], b_[ST], w_[ST];
 #pragma unroll
                 for (int u = 0; u < ST; ++u) {
@@ -435,8 +434,8 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                     } else {
                         Wq = qmul(lam, qconj(PL[u]));
                     }
-                    a_[u] = Wq.b * rowL.x + Wq.c * rowL.z;
-                    b_[u] = Wq.c * rowL.x - Wq.b * rowL.z;
+                    a_[u] = Wq.b * rowL.x + Wq.c * rowL.y;
+                    b_[u] = Wq.c * rowL.x - Wq.b * rowL.y;
                     w_[u] = Wq.d;
                 }
 #pragma unroll
@@ -453,8 +452,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
 #pragma unroll
                 for (int e = NB - 1; e >= 0; --e) {
                     const float4 row = bwd4[rb + jb * NB + e];
-                    const float2 tt = tau2[rb + jb * NB + e];
-                    const F2 cd = f2(row.x, row.y), sd = f2(row.z, row.w), tau = f2(tt.x, tt.y);
+                    const F2 cd = f2b(row.x), sd = f2b(row.y), tau = f2b(row.z);
                     F2 gp = f2b(0.0f), gt = f2b(0.0f);
                     F2 h[NP], s[NP], c[NP], s2[NP], C2[NP], Sr[NP], k1_[NP], t[NP], uu[NP], K[NP], BS[NP], A1[NP], B1[NP], Wz[NP];
                     int kb[ST];
