@@ -455,6 +455,18 @@ def other_configs(uq, ops, dev):
     buf4 = torch.empty(B + B * L * 3, device=dev)
     ms = timed(lambda: ops._su4_launch(True, p4, tgt, None, None, M, 0, 1.0, (1.0, 0.05), 7, 0, None, None, None, buf4[:B], buf4[B:], 0), 5)
     out["c4_su4_B1_L128_M32768_fwdbwd"] = {"su4_prop_per_s": B * M * L / (ms * 1e-3), "ms": ms}
+    # stock-torch-on-the-same-B200 (informative): the reference's ATen op sequence (oracle/torch_port.py) on cuda:0
+    try:
+        from oracle import torch_port as tp
+        Bt, Lt, Mt = 1, 256, 16384
+        pt = torch.stack([(torch.rand(Bt, Lt, generator=g) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(Bt, Lt, generator=g)], -1).to(dev)
+        Tt = torch.eye(2, dtype=torch.complex64, device=dev)[None]
+        et = uq.philox_errors(Bt, Mt, (1.0, 0.05), 3, 0, device=dev)
+        ms = timed(lambda: tp.train_step_loss_and_grad(pt, Tt, et, Mt), 3)
+        out["reference_op_sequence_on_this_B200_B1_L256_M16384_fwdbwd"] = {"prop_per_s": Bt * Mt * Lt / (ms * 1e-3), "ms": ms,
+                                                                           "note": "torch.linalg.matrix_exp + bmm tree + autograd, complex64, cuda"}
+    except Exception as e:  # informative only
+        out["reference_op_sequence_on_this_B200_B1_L256_M16384_fwdbwd"] = {"error": repr(e)[:200]}
     wl = make_workload("curriculum", dev)
     B, L, M = 512, wl["L"], wl["M"]
     p = wl["pulses"][:B].double().to(dev)
