@@ -49,6 +49,8 @@ extern "C" {
 #define UQOC_FLAG_NO_TABLE 4u    /* packed kernel: polynomial sin/cos instead of the shared-memory table */
 #define UQOC_FLAG_WPS4 16u       /* packed kernel: force the pulse train to be split over the block's 4 warps */
 #define UQOC_FLAG_WPS1 32u       /* packed kernel: force one warp per sample group */
+#define UQOC_FLAG_SU4_PADE 64u   /* SU(4): per-pulse scaling-and-squaring exponential kernel instead of the default
+                                    eigenframe kernel (one real-symmetric eigendecomposition per error sample) */
 /* tuning overrides (0 = let the library choose): samples per thread (1,2,4) and lanes per
  * sample (1,2,4,8,16,32) of the shared-pulse kernels */
 #define UQOC_FLAG_ST(n) (((unsigned)(n) & 0xFu) << 8)

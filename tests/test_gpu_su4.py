@@ -25,9 +25,13 @@ def _case(seed, B, L, M, J=1.0, sd=1.0):
     return pulses, err, T
 
 
+PADE = [False, True]      # default eigenframe kernel / per-pulse scaling-and-squaring kernel (UQOC_FLAG_SU4_PADE)
+
+
+@pytest.mark.parametrize("pade", PADE)
 @pytest.mark.parametrize("dtype,tolF,tolG", [(torch.float64, 1e-12, 1e-10), (torch.float32, 1e-5, 1e-4)])
-@pytest.mark.parametrize("L,M,splits", [(1, 5, 0), (7, 70, 0), (33, 130, 3), (128, 64, 0)])
-def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits):
+@pytest.mark.parametrize("L,M,splits", [(1, 5, 0), (7, 70, 0), (33, 130, 3), (128, 64, 0), (400, 96, 0)])
+def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits, pade):
     B, J = 3, 0.8
     pulses, err, T = _case(L, B, L, M, J)
     if dtype == torch.float32:
@@ -36,7 +40,7 @@ def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits):
     p = _t(pulses, dtype).requires_grad_(True)
     F = torch.empty(B * M, dtype=dtype, device=DEV)
     loss, mf = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err, dtype), monte_carlo=M, J=J, F_out=F,
-                                           flags=uq.tuning_flags(splits=splits))
+                                           flags=uq.tuning_flags(splits=splits, su4_pade=pade))
     loss.backward()
     assert np.abs(F.cpu().numpy() - want_F).max() < tolF
     assert abs(loss.item() - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
@@ -45,7 +49,8 @@ def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits):
     assert np.abs(mf.cpu().numpy() - want_F.reshape(B, M).mean(1)).max() < 10 * tolF
 
 
-def test_su4_general_target_and_large_detuning():
+@pytest.mark.parametrize("pade", PADE)
+def test_su4_general_target_and_large_detuning(pade):
     B, L, M, J = 2, 20, 40, 1.3
     pulses, err, T = _case(3, B, L, M, J, sd=2.5)            # |delta| up to ~7: several squarings
     rng = np.random.default_rng(9)
@@ -53,29 +58,32 @@ def test_su4_general_target_and_large_detuning():
     want_l, want_g, want_F = orc.su4_loss_and_grad(pulses, T, err, M, J, "nll")
     p = _t(pulses).requires_grad_(True)
     F = torch.empty(B * M, dtype=torch.float64, device=DEV)
-    loss, _ = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err), monte_carlo=M, J=J, loss="nll", F_out=F)
+    loss, _ = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err), monte_carlo=M, J=J, loss="nll", F_out=F,
+                                          flags=uq.tuning_flags(su4_pade=pade))
     loss.backward()
     assert np.abs(F.cpu().numpy() - want_F).max() < 1e-11
     assert abs(loss.item() - want_l) < 1e-11
     assert np.abs(p.grad.cpu().numpy() - want_g).max() / np.abs(want_g).max() < 1e-10
 
 
-def test_su4_generator_and_generic_fidelity():
+@pytest.mark.parametrize("pade", PADE)
+def test_su4_generator_and_generic_fidelity(pade):
+    fl = uq.tuning_flags(su4_pade=pade)
     B, L, M, J = 1, 16, 50, 1.0
     pulses, err, T = _case(4, B, L, M, J)
     want_U = orc.su4_unitary_generator(np.repeat(pulses, M, 0), err, J)
     for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 3e-6)):
         pl = _t(pulses, dtype)
-        U = uq.su4_unitary_generator(pl.expand(M, -1, -1), _t(err, dtype), J)          # shared pulse train
+        U = uq.su4_unitary_generator(pl.expand(M, -1, -1), _t(err, dtype), J, fl)      # shared pulse train
         assert U.shape == (M, 4, 4)
         assert np.abs(U.cpu().numpy() - want_U).max() < tol
-        U2 = uq.su4_unitary_generator(pl.expand(M, -1, -1).contiguous(), _t(err, dtype), J)   # per-sample rows
+        U2 = uq.su4_unitary_generator(pl.expand(M, -1, -1).contiguous(), _t(err, dtype), J, fl)   # per-sample rows
         assert np.abs(U2.cpu().numpy() - want_U).max() < tol
         F = uq.fidelity(U, _t(T).expand(M, -1, -1), 2)                                  # d = 4 (SCORE.py:181-183)
         want_F = orc.fidelity(want_U, np.repeat(T, M, 0), 2)
         assert np.abs(F.cpu().numpy() - want_F).max() < 10 * tol
     # J = 0 factorises into two independent SU(2) propagators
-    U0 = uq.su4_unitary_generator(_t(pulses).expand(M, -1, -1), _t(err), 0.0).cpu().numpy()
+    U0 = uq.su4_unitary_generator(_t(pulses).expand(M, -1, -1), _t(err), 0.0, fl).cpu().numpy()
     p1 = np.repeat(pulses[:, :, [0, 2]], M, 0)
     p2 = np.repeat(pulses[:, :, [1, 2]], M, 0)
     # SU(2) oracle scales delta by (1+eps) like the SU(4) definition does
@@ -102,6 +110,41 @@ def test_su4_philox_stream_and_sharding():
     want_l, want_g, _ = orc.su4_loss_and_grad(pulses, T, err_out.cpu().numpy(), M, 1.0)
     assert abs(loss.item() - want_l) < 1e-11
     assert np.abs(p.grad.cpu().numpy() - want_g).max() / np.abs(want_g).max() < 1e-10
+
+
+def test_su4_degenerate_spectrum():
+    """delta1 = delta2 = 0 and J = 0 make 2H' = XI + IX doubly degenerate: the Jacobi basis is then arbitrary
+    inside the degenerate subspace, the propagator must not be."""
+    B, L, M = 2, 9, 6
+    pulses, err, T = _case(11, B, L, M, 0.0)
+    err[:2] = 0.0
+    err[0, 3] = 1e-9                                          # nearly degenerate
+    want_l, want_g, want_F = orc.su4_loss_and_grad(pulses, T, err, M, 0.0, "sharp")
+    p = _t(pulses).requires_grad_(True)
+    F = torch.empty(B * M, dtype=torch.float64, device=DEV)
+    loss, _ = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err), monte_carlo=M, J=0.0, F_out=F)
+    loss.backward()
+    assert np.abs(F.cpu().numpy() - want_F).max() < 1e-12
+    assert np.abs(p.grad.cpu().numpy() - want_g).max() / np.abs(want_g).max() < 1e-10
+
+
+def test_su4_kernels_agree_fp32_long_train():
+    """FP32 eigenframe kernel against the FP64 kernel at L = 512 (coherent rounding of V / mu would show here)."""
+    torch.manual_seed(1)
+    B, L, M, J = 2, 512, 2048, 1.0
+    pulses = torch.stack([(torch.rand(B, L) * 2 - 1) * 3.15, (torch.rand(B, L) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(B, L)], -1).to(DEV)
+    T = torch.diag(torch.tensor([1, 1, 1, -1], dtype=torch.complex64)).to(DEV)[None].expand(B, -1, -1)
+    err = uq.philox_errors_su4(B, M, (1.0, 0.05), seed=5)
+    F32 = torch.empty(B * M, device=DEV)
+    F64 = torch.empty(B * M, device=DEV, dtype=torch.float64)
+    p32 = pulses.clone().requires_grad_(True)
+    l32, _ = uq.fused_propagate_loss_su4(p32, T, error=err, monte_carlo=M, J=J, F_out=F32)
+    l32.backward()
+    p64 = pulses.double().requires_grad_(True)
+    l64, _ = uq.fused_propagate_loss_su4(p64, T, error=err.double(), monte_carlo=M, J=J, F_out=F64)
+    l64.backward()
+    assert (F32.double() - F64).abs().max().item() < 1e-5
+    assert ((p32.grad.double() - p64.grad).abs().max() / p64.grad.abs().max()).item() < 1e-4
 
 
 def test_su4_config4_sized_properties():

@@ -221,6 +221,10 @@ __device__ __forceinline__ void philox_su4<double>(uint64_t j, uint32_t b, uint6
     d2 = sig_d * r1 * c1;
 }
 
+}  // namespace uqoc
+#include "uqoc_su4_eig.cuh"
+namespace uqoc {
+
 constexpr int kSu4Threads = 64;
 constexpr int kSu4Warps = kSu4Threads / 32;
 
@@ -394,7 +398,10 @@ static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fla
     const int fsp = (flags >> 18) & 0xFFF;
     if (fsp) splits = fsp < pl.n_tiles ? fsp : pl.n_tiles;
     pl.splits = (int)splits;
-    pl.smem = dtype == UQOC_F64 ? su4_smem_bytes<double>((int)L, bwd) : su4_smem_bytes<float>((int)L, bwd);
+    if (flags & UQOC_FLAG_SU4_PADE)
+        pl.smem = dtype == UQOC_F64 ? su4_smem_bytes<double>((int)L, bwd) : su4_smem_bytes<float>((int)L, bwd);
+    else
+        pl.smem = dtype == UQOC_F64 ? su4e_smem_bytes<double>((int)L, bwd) : su4e_smem_bytes<float>((int)L, bwd);
     return pl;
 }
 
@@ -422,7 +429,8 @@ static int su4_run(const void* pulses, const void* target, const void* err, cons
         p.Fsum_part = (T*)Fsum;
         p.G_part = (T*)G;
     }
-    auto kern = su4_kernel<T, BWD>;
+    static_assert(kSu4Threads == kSu4eThreads, "both SU(4) kernels share the launch plan");
+    auto kern = (flags & UQOC_FLAG_SU4_PADE) ? su4_kernel<T, BWD> : su4e_kernel<T, BWD>;
     if (pl.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         if (e != cudaSuccess) {

@@ -1,0 +1,490 @@
+// Two-qubit SU(4) path, "eigenframe" kernel (sm_100a) -- the default SU(4) kernel.
+//
+// NOT IN THE REFERENCE: builder-defined contract, see uqoc_su4.cu.
+//
+// Static disorder makes every pulse of one error sample the SAME Hamiltonian up to a local z-frame:
+//   H_k = R_k H' R_k^dagger,   R_k = exp(-i phi1_k ZI/2) exp(-i phi2_k IZ/2)   (diagonal phases),
+//   2H' = XI + IX + d1 ZI + d2 IZ + J ZZ                                        (REAL symmetric, pulse-independent).
+// So 2H' = V diag(mu) V^T is diagonalised ONCE per sample (cyclic Jacobi in double, ~4 pulses' worth of
+// work) and each pulse is exact and cheap:
+//   U_k = R_k V D_k V^T R_k^dagger,   D_k = diag exp(-i mu_m tau_k (1+eps) / 2).
+// With the state kept in the pulse's own frame, Q_k = R_k^dagger P_k,
+//   Q_k = V D_k V^T G_k Q_{k-1},   G_k = R_k^dagger R_{k-1} = diag exp(+-i (dphi1 +- dphi2)/2)   (pulse-only),
+// i.e. two real-times-complex 4x4 products and two diagonal phase multiplications: 384 FMA-pipe operations
+// + 4 sin/cos per (pulse, sample) instead of ~1700 for the scaling-and-squaring exponential.
+//
+// Backward: the Pade kernel's B_k = P_k W_k^dagger enters every gradient only through Im Tr(B_k X) with X
+// Hermitian, so only the Hermitian matrix A_k = (B_k - B_k^dagger)/(2i) is carried (16 reals).  In frame k
+//   dF/dtau_k  = (1+eps)/2 sum_m mu_m (V^T A_k V)_mm,
+//   dF/dphi1_k = 1/2 [Tr(A_k ZI) - Tr(X_k ZI)],   X_k = V D_k^dagger (V^T A_k V) D_k V^T,
+//   A_{k-1} = G_k^dagger X_k G_k.
+// Conjugation by the REAL V splits into a symmetric and an antisymmetric real problem (176 operations
+// instead of 512); the diagonal conjugations touch the 6 off-diagonal pairs only.
+// FP32: V is rounded from the double Jacobi result, the eigenvalues are carried as hi + lo floats (the
+// rounding of mu would otherwise be a systematic phase error multiplied by L), and Q_L gets one
+// Newton-Schulz step (removes, to first order, the norm drift caused by V_f^T V_f = I + O(6e-8)).
+#pragma once
+#include "uqoc_su2_kernels.cuh"
+
+namespace uqoc {
+
+// ------------------------------------------------------------------ Jacobi eigensolver, 4x4 real symmetric
+// A = 2H' (d1, d2, J);  on exit V[i][m] = component i of eigenvector m, mu[m] its eigenvalue.
+// Fully unrolled (all indices compile-time); the sweep loop is warp-uniform (callers are converged).
+__device__ __forceinline__ void su4_jacobi(double d1, double d2, double J, double (&V)[4][4], double (&mu)[4]) {
+    double A[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            A[i][j] = 0.0;
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    A[0][0] = d1 + d2 + J; A[1][1] = d1 - d2 - J; A[2][2] = -d1 + d2 - J; A[3][3] = -d1 - d2 + J;
+    A[0][1] = A[1][0] = 1.0; A[2][3] = A[3][2] = 1.0;      // IX
+    A[0][2] = A[2][0] = 1.0; A[1][3] = A[3][1] = 1.0;      // XI
+    const double scale = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2] + A[3][3] * A[3][3] + 8.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[0][3] * A[0][3] + A[1][2] * A[1][2] +
+                           A[1][3] * A[1][3] + A[2][3] * A[2][3];
+        if (__all_sync(0xffffffffu, off <= 1e-32 * scale)) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = A[p][q];
+                if (fabs(apq) > 1e-290) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = copysign(1.0, theta) / (fabs(theta) + ::sqrt(::fma(theta, theta, 1.0)));
+                    const double c = ::rsqrt(::fma(t, t, 1.0));
+                    const double s = t * c;
+                    A[p][p] -= t * apq;
+                    A[q][q] += t * apq;
+                    A[p][q] = A[q][p] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r != p && r != q) {
+                            const double arp = A[r][p], arq = A[r][q];
+                            A[r][p] = A[p][r] = c * arp - s * arq;
+                            A[r][q] = A[q][r] = s * arp + c * arq;
+                        }
+                        const double vrp = V[r][p], vrq = V[r][q];
+                        V[r][p] = c * vrp - s * vrq;
+                        V[r][q] = s * vrp + c * vrq;
+                    }
+                }
+            }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) mu[m] = A[m][m];
+}
+
+// per-sample data of the eigenframe kernel
+template <typename T>
+struct Su4Frame {
+    T V[4][4];       // V[i][m]
+    T lam[4];        // mu/2 (hi part in FP32)
+    T lam_lo[4];     // FP32: mu/2 - float(mu/2);  FP64: 0
+    T te;            // 1 + eps
+};
+
+template <typename T>
+__device__ __forceinline__ void su4_make_frame(Su4Frame<T>& f, T d1, T d2, T eps, T J) {
+    double V[4][4], mu[4];
+    su4_jacobi((double)d1, (double)d2, (double)J, V, mu);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) f.V[i][m] = (T)V[i][m];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const double l = 0.5 * mu[m];
+        f.lam[m] = (T)l;
+        f.lam_lo[m] = (T)(l - (double)f.lam[m]);
+    }
+    f.te = (T)1 + eps;
+}
+
+// full-sign sin/cos of the eigenphases.  FP32: the mod-pi polynomial pair of uqoc_common.cuh with the sign
+// (-1)^k restored by an integer XOR (ALU pipe); FP64: libm.
+__device__ __forceinline__ void su4_sincos(float h, float& s, float& c) {
+    int kb;
+    sincos_modpi(h, s, c, kb);
+    const int sg = kb << 31;
+    s = __int_as_float(__float_as_int(s) ^ sg);
+    c = __int_as_float(__float_as_int(c) ^ sg);
+}
+__device__ __forceinline__ void su4_sincos(double h, double& s, double& c) { ::sincos(h, &s, &c); }
+
+template <typename T>
+__device__ __forceinline__ void su4_phases(const Su4Frame<T>& f, T tau, T (&c)[4], T (&s)[4]) {
+    const T t = tau * f.te;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        T h;
+        if constexpr (sizeof(T) == 4) h = fmaf(f.lam[m], t, f.lam_lo[m] * t);
+        else h = f.lam[m] * t;
+        su4_sincos(h, s[m], c[m]);
+    }
+}
+
+// ------------------------------------------------------------------ forward step  Q <- V D V^T G Q
+// g = {cos a, sin a, cos b, sin b}: G = diag(e^{ia}, e^{ib}, e^{-ib}, e^{-ia}), a = (dphi1+dphi2)/2, b = (dphi1-dphi2)/2
+template <typename T>
+__device__ __forceinline__ void su4e_fwd_step(T (&qr)[4][4], T (&qi)[4][4], const Su4Frame<T>& f, const T (&c)[4],
+                                              const T (&s)[4], T ca, T sa, T cb, T sb) {
+    T xr[4][4], xi[4][4];
+    // G Q (row phases)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        xr[0][j] = ca * qr[0][j] - sa * qi[0][j]; xi[0][j] = ca * qi[0][j] + sa * qr[0][j];
+        xr[1][j] = cb * qr[1][j] - sb * qi[1][j]; xi[1][j] = cb * qi[1][j] + sb * qr[1][j];
+        xr[2][j] = cb * qr[2][j] + sb * qi[2][j]; xi[2][j] = cb * qi[2][j] - sb * qr[2][j];
+        xr[3][j] = ca * qr[3][j] + sa * qi[3][j]; xi[3][j] = ca * qi[3][j] - sa * qr[3][j];
+    }
+    // Y = V^T X, then D Y (row m times c_m - i s_m)
+    T yr[4][4], yi[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const T ar = f.V[0][m] * xr[0][j] + f.V[1][m] * xr[1][j] + f.V[2][m] * xr[2][j] + f.V[3][m] * xr[3][j];
+            const T ai = f.V[0][m] * xi[0][j] + f.V[1][m] * xi[1][j] + f.V[2][m] * xi[2][j] + f.V[3][m] * xi[3][j];
+            yr[m][j] = c[m] * ar + s[m] * ai;
+            yi[m][j] = c[m] * ai - s[m] * ar;
+        }
+    // Q = V Y
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            qr[i][j] = f.V[i][0] * yr[0][j] + f.V[i][1] * yr[1][j] + f.V[i][2] * yr[2][j] + f.V[i][3] * yr[3][j];
+            qi[i][j] = f.V[i][0] * yi[0][j] + f.V[i][1] * yi[1][j] + f.V[i][2] * yi[2][j] + f.V[i][3] * yi[3][j];
+        }
+}
+
+// ------------------------------------------------------------------ Hermitian 4x4 in packed form
+// A = S + iK, S symmetric (dg + re), K antisymmetric (im, upper triangle).  Pair index of (i<j):
+// (0,1)=0 (0,2)=1 (0,3)=2 (1,2)=3 (1,3)=4 (2,3)=5.
+template <typename T>
+struct Herm4 {
+    T dg[4], re[6], im[6];
+};
+__host__ __device__ constexpr int su4_pair(int i, int j) { return i == 0 ? j - 1 : (i == 1 ? j + 1 : 5); }
+
+// sym[i][j] / asym[i][j] accessors with compile-time indices
+template <typename T>
+__device__ __forceinline__ T herm_s(const Herm4<T>& A, int i, int j) {
+    return i == j ? A.dg[i] : (i < j ? A.re[su4_pair(i, j)] : A.re[su4_pair(j, i)]);
+}
+template <typename T>
+__device__ __forceinline__ T herm_k(const Herm4<T>& A, int i, int j) {
+    return i == j ? (T)0 : (i < j ? A.im[su4_pair(i, j)] : -A.im[su4_pair(j, i)]);
+}
+
+// E = W^T A W with W[i][m] = TR ? V[m][i] : V[i][m]   (TR = false: into the eigenbasis; true: back out)
+template <typename T, bool TR>
+__device__ __forceinline__ void herm_conj_real(Herm4<T>& E, const Herm4<T>& A, const Su4Frame<T>& f) {
+    T ys[4][4], yk[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            T a = (T)0, b = (T)0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const T w = TR ? f.V[m][j] : f.V[j][m];
+                a += herm_s(A, i, j) * w;
+                if (j != i) b += herm_k(A, i, j) * w;
+            }
+            ys[i][m] = a;
+            yk[i][m] = b;
+        }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = m; n < 4; ++n) {
+            T a = (T)0, b = (T)0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const T w = TR ? f.V[m][i] : f.V[i][m];
+                a += w * ys[i][n];
+                if (n != m) b += w * yk[i][n];
+            }
+            if (n == m) E.dg[m] = a;
+            else {
+                E.re[su4_pair(m, n)] = a;
+                E.im[su4_pair(m, n)] = b;
+            }
+        }
+}
+
+// ------------------------------------------------------------------ kernel
+constexpr int kSu4eThreads = 64;
+constexpr int kSu4eWarps = kSu4eThreads / 32;
+
+// shared memory: per pulse {fw[4], tau, b1[4], b2[4]} + target' (32) + last-frame phases (8) + scratch + acc
+template <typename T>
+__host__ __device__ inline size_t su4e_smem_bytes(int L, bool bwd) {
+    size_t n = (size_t)L * (bwd ? 13 : 5) + 32 + 8 + kSu4eWarps;
+    if (bwd) n += (size_t)kSu4eWarps * L * 3;
+    return n * sizeof(T) + 16;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = p.L;
+    T* fw = reinterpret_cast<T*>(smem_raw);                 // [L][4]  cos a, sin a, cos b, sin b
+    T* b1 = fw + (size_t)L * 4;                             // [L][4]  cos dphi1, sin dphi1, cos dphi2, sin dphi2
+    T* b2 = b1 + (BWD ? (size_t)L * 4 : 0);                 // [L][4]  cos(d1+d2), sin(d1+d2), cos(d1-d2), sin(d1-d2)
+    T* tauv = b2 + (BWD ? (size_t)L * 4 : 0);               // [L]
+    T* tgt = tauv + L;                                      // [32]    T' = R_L^dagger T
+    T* rl = tgt + 32;                                       // [8]     last-frame phases e^{i gamma_i}
+    T* scratch = rl + 8;                                    // [warps]
+    T* acc = scratch + kSu4eWarps;                          // [warps][L][3]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int split = blockIdx.x % p.splits, b = blockIdx.x / p.splits;
+    {
+        const T* pb = p.pulses + (size_t)b * L * 3;
+        for (int i = tid; i < L; i += kSu4eThreads) {
+            const double p1 = (double)pb[3 * i], p2 = (double)pb[3 * i + 1];
+            const double q1 = i > 0 ? (double)pb[3 * i - 3] : 0.0, q2 = i > 0 ? (double)pb[3 * i - 2] : 0.0;
+            const double e1 = p1 - q1, e2 = p2 - q2;
+            double sa, ca, sb, cb;
+            ::sincos(0.5 * (e1 + e2), &sa, &ca);
+            ::sincos(0.5 * (e1 - e2), &sb, &cb);
+            fw[4 * i] = (T)ca; fw[4 * i + 1] = (T)sa; fw[4 * i + 2] = (T)cb; fw[4 * i + 3] = (T)sb;
+            tauv[i] = pb[3 * i + 2];
+            if (BWD) {
+                // e^{i dphi1} = e^{ia} e^{ib}, e^{i dphi2} = e^{ia} e^{-ib}, e^{i(d1+d2)} = e^{2ia}, e^{i(d1-d2)} = e^{2ib}
+                b1[4 * i] = (T)(ca * cb - sa * sb); b1[4 * i + 1] = (T)(sa * cb + ca * sb);
+                b1[4 * i + 2] = (T)(ca * cb + sa * sb); b1[4 * i + 3] = (T)(sa * cb - ca * sb);
+                b2[4 * i] = (T)(ca * ca - sa * sa); b2[4 * i + 1] = (T)(2.0 * sa * ca);
+                b2[4 * i + 2] = (T)(cb * cb - sb * sb); b2[4 * i + 3] = (T)(2.0 * sb * cb);
+            }
+        }
+        if (tid < 16) {
+            // T'[i][j] = e^{+i gamma_i} T[i][j], gamma = ((p1+p2)/2, (p1-p2)/2, -(p1-p2)/2, -(p1+p2)/2) of the LAST pulse
+            const int i = tid >> 2;
+            const double p1 = (double)pb[3 * (L - 1)], p2 = (double)pb[3 * (L - 1) + 1];
+            const double gam = (i == 0) ? 0.5 * (p1 + p2) : (i == 1) ? 0.5 * (p1 - p2) : (i == 2) ? -0.5 * (p1 - p2) : -0.5 * (p1 + p2);
+            double sg, cg;
+            ::sincos(gam, &sg, &cg);
+            const double tr_ = (double)p.target[(size_t)b * 32 + 2 * tid], ti_ = (double)p.target[(size_t)b * 32 + 2 * tid + 1];
+            tgt[2 * tid] = (T)(cg * tr_ - sg * ti_);
+            tgt[2 * tid + 1] = (T)(cg * ti_ + sg * tr_);
+            if ((tid & 3) == 0) {
+                rl[2 * i] = (T)cg;
+                rl[2 * i + 1] = (T)sg;
+            }
+        }
+        if (BWD)
+            for (int i = tid; i < kSu4eWarps * L * 3; i += kSu4eThreads) acc[i] = (T)0;
+    }
+    __syncthreads();
+    const size_t Bm = (size_t)p.B * p.M;
+    T fsum = (T)0;
+    for (int tile = split; tile < p.n_tiles; tile += p.splits) {
+        const long long j = (long long)tile * kSu4eThreads + tid;
+        const bool valid = j < p.M;
+        const size_t sidx = (size_t)b * p.M + (size_t)(valid ? j : 0);
+        Su4Frame<T> f;
+        {
+            T d1 = (T)0, d2 = (T)0, eps = (T)0;
+            if (valid) {
+                if (p.err != nullptr) {
+                    d1 = p.err[sidx]; d2 = p.err[Bm + sidx]; eps = p.err[2 * Bm + sidx];
+                } else {
+                    philox_su4<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, d1, d2, eps);
+                }
+                if (p.err_out != nullptr) {
+                    p.err_out[sidx] = d1; p.err_out[Bm + sidx] = d2; p.err_out[2 * Bm + sidx] = eps;
+                }
+            }
+            su4_make_frame<T>(f, d1, d2, eps, p.J);
+        }
+        // ---------------- forward ----------------
+        T qr[4][4], qi[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                qr[i][jj] = (i == jj) ? (T)1 : (T)0;
+                qi[i][jj] = (T)0;
+            }
+        for (int k = 0; k < L; ++k) {
+            T c[4], s[4];
+            su4_phases<T>(f, tauv[k], c, s);
+            su4e_fwd_step<T>(qr, qi, f, c, s, fw[4 * k], fw[4 * k + 1], fw[4 * k + 2], fw[4 * k + 3]);
+        }
+        if constexpr (sizeof(T) == 4) {
+            // one Newton-Schulz step  Q <- Q (3I - Q^dagger Q)/2
+            T nr[4][4], ni[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    T ar = (T)0, ai = (T)0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ar += qr[k][i] * qr[k][jj] + qi[k][i] * qi[k][jj];
+                        ai += qr[k][i] * qi[k][jj] - qi[k][i] * qr[k][jj];
+                    }
+                    nr[i][jj] = (T)0.5 * (((i == jj) ? (T)1 : (T)0) - ar);
+                    ni[i][jj] = (T)-0.5 * ai;
+                }
+            T ur[4][4], ui[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    T ar = qr[i][jj], ai = qi[i][jj];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ar += qr[i][k] * nr[k][jj] - qi[i][k] * ni[k][jj];
+                        ai += qr[i][k] * ni[k][jj] + qi[i][k] * nr[k][jj];
+                    }
+                    ur[i][jj] = ar;
+                    ui[i][jj] = ai;
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    qr[i][jj] = ur[i][jj];
+                    qi[i][jj] = ui[i][jj];
+                }
+        }
+        T trr = (T)0, tri = (T)0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const T t_r = tgt[2 * (4 * i + jj)], t_i = tgt[2 * (4 * i + jj) + 1];
+                trr += qr[i][jj] * t_r + qi[i][jj] * t_i;
+                tri += qr[i][jj] * t_i - qi[i][jj] * t_r;
+            }
+        const T F = (trr * trr + tri * tri + (T)4) * (T)0.05;
+        if (valid) {
+            fsum += F;
+            if (p.F_out != nullptr) p.F_out[sidx] = F;
+            if (!BWD && p.U_out != nullptr) {
+                // P_L = R_L Q_L: row i times e^{-i gamma_i}
+                T* U = p.U_out + sidx * 32;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const T cg = rl[2 * i], sg = rl[2 * i + 1];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        U[2 * (4 * i + jj)] = cg * qr[i][jj] + sg * qi[i][jj];
+                        U[2 * (4 * i + jj) + 1] = cg * qi[i][jj] - sg * qr[i][jj];
+                    }
+                }
+            }
+        }
+        if constexpr (BWD) {
+            // C = (tr/10) w Q T'^dagger;  A = (C - C^dagger)/(2i):  S = (Ci + Ci^T)/2,  K = -(Cr - Cr^T)/2
+            T wgt = (T)0;
+            if (valid) wgt = p.weight != nullptr ? p.weight[sidx] : (T)1;
+            Herm4<T> A;
+            {
+                const T fr = wgt * trr * (T)0.1, fi = wgt * tri * (T)0.1;
+                T cr_[4][4], ci_[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        T mr = (T)0, mi = (T)0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const T t_r = tgt[2 * (4 * jj + k)], t_i = tgt[2 * (4 * jj + k) + 1];
+                            mr += qr[i][k] * t_r + qi[i][k] * t_i;
+                            mi += qi[i][k] * t_r - qr[i][k] * t_i;
+                        }
+                        cr_[i][jj] = fr * mr - fi * mi;
+                        ci_[i][jj] = fr * mi + fi * mr;
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    A.dg[i] = ci_[i][i];
+#pragma unroll
+                    for (int jj = i + 1; jj < 4; ++jj) {
+                        A.re[su4_pair(i, jj)] = (T)0.5 * (ci_[i][jj] + ci_[jj][i]);
+                        A.im[su4_pair(i, jj)] = (T)-0.5 * (cr_[i][jj] - cr_[jj][i]);
+                    }
+                }
+            }
+            for (int k = L - 1; k >= 0; --k) {
+                T c[4], s[4];
+                su4_phases<T>(f, tauv[k], c, s);
+                const T z1a = A.dg[0] + A.dg[1] - A.dg[2] - A.dg[3];
+                const T z2a = A.dg[0] - A.dg[1] + A.dg[2] - A.dg[3];
+                Herm4<T> E;
+                herm_conj_real<T, false>(E, A, f);
+                T g_tau = f.te * (E.dg[0] * f.lam[0] + E.dg[1] * f.lam[1] + E.dg[2] * f.lam[2] + E.dg[3] * f.lam[3]);
+                // E'_mn = E_mn e^{i(h_m - h_n)}
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int n = m + 1; n < 4; ++n) {
+                        const T wr = c[m] * c[n] + s[m] * s[n], wi = s[m] * c[n] - c[m] * s[n];
+                        const int pq = su4_pair(m, n);
+                        const T er = E.re[pq], ei = E.im[pq];
+                        E.re[pq] = er * wr - ei * wi;
+                        E.im[pq] = er * wi + ei * wr;
+                    }
+                Herm4<T> X;
+                herm_conj_real<T, true>(X, E, f);
+                const T z1b = X.dg[0] + X.dg[1] - X.dg[2] - X.dg[3];
+                const T z2b = X.dg[0] - X.dg[1] + X.dg[2] - X.dg[3];
+                T g_p1 = (T)0.5 * (z1a - z1b), g_p2 = (T)0.5 * (z2a - z2b);
+                // A_{k-1} = G^dagger X G:  X_ij e^{-i(gamma_i - gamma_j)}
+                {
+                    const T c1 = b1[4 * k], s1 = b1[4 * k + 1], c2 = b1[4 * k + 2], s2 = b1[4 * k + 3];
+                    const T cp = b2[4 * k], sp = b2[4 * k + 1], cm = b2[4 * k + 2], sm = b2[4 * k + 3];
+                    const T pc[6] = {c2, c1, cp, cm, c1, c2};
+                    const T ps[6] = {s2, s1, sp, sm, s1, s2};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) A.dg[e] = X.dg[e];
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) {
+                        A.re[e] = X.re[e] * pc[e] + X.im[e] * ps[e];
+                        A.im[e] = X.im[e] * pc[e] - X.re[e] * ps[e];
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    g_p1 += __shfl_xor_sync(0xffffffffu, g_p1, d);
+                    g_p2 += __shfl_xor_sync(0xffffffffu, g_p2, d);
+                    g_tau += __shfl_xor_sync(0xffffffffu, g_tau, d);
+                }
+                if (lane == 0) {
+                    T* dst = acc + ((size_t)warp * L + k) * 3;
+                    dst[0] += g_p1; dst[1] += g_p2; dst[2] += g_tau;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+    if (lane == 0) scratch[warp] = fsum;
+    __syncthreads();
+    if (tid == 0 && p.Fsum_part != nullptr) {
+        T tot = (T)0;
+#pragma unroll
+        for (int w = 0; w < kSu4eWarps; ++w) tot += scratch[w];
+        p.Fsum_part[(size_t)split * p.B + b] = tot;
+    }
+    if constexpr (BWD) {
+        T* gout = p.G_part + ((size_t)split * p.B + b) * L * 3;
+        for (int i = tid; i < 3 * L; i += kSu4eThreads) {
+            T tot = (T)0;
+#pragma unroll
+            for (int w = 0; w < kSu4eWarps; ++w) tot += acc[(size_t)w * L * 3 + i];
+            gout[i] = tot;
+        }
+    }
+}
+
+}  // namespace uqoc

@@ -74,10 +74,11 @@ def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:
 
 
 def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool = False, no_packed: bool = False,
-                 no_table: bool = False, wps: int = 0) -> int:
+                 no_table: bool = False, wps: int = 0, su4_pade: bool = False) -> int:
     """Pack the launch-shape overrides of include/uqoc.h (0 = library heuristic)."""
     return ((FLAG_FAST_SINCOS if fast_sincos else 0) | (2 if no_packed else 0) | (4 if no_table else 0)
-            | (16 if wps == 4 else 0) | (32 if wps == 1 else 0) | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
+            | (16 if wps == 4 else 0) | (32 if wps == 1 else 0) | (64 if su4_pade else 0)
+            | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
             | ((splits & 0xFFF) << 18))
 
 
@@ -516,7 +517,7 @@ def fused_propagate_loss_su4(pulses: torch.Tensor, U_target: torch.Tensor, *, er
                                         F_out, err_out)
 
 
-def su4_unitary_generator(pulses: torch.Tensor, error: torch.Tensor, J: float = 1.0) -> torch.Tensor:
+def su4_unitary_generator(pulses: torch.Tensor, error: torch.Tensor, J: float = 1.0, flags: int = 0) -> torch.Tensor:
     """Two-qubit generator with the reference's calling convention: pulses (Bm, L, 3), error (3, Bm) ->
     (Bm, 4, 4) complex.  Forward only.  ``expand``-ed (stride-0) pulses share one staged pulse train;
     materialised per-sample rows are run one target per block (correct, not tuned)."""
@@ -534,10 +535,11 @@ def su4_unitary_generator(pulses: torch.Tensor, error: torch.Tensor, J: float = 
     if Bm > 1 and pulses.stride(0) == 0:
         tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None], rdt, 1)
         _su4_launch(False, pulses[0:1].to(rdt).contiguous(), tgt, err, None, Bm, 0, J, (0.0, 0.0), 0, 0, U, None, None, None,
-                    None, 0)
+                    None, flags)
     else:
         tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None].expand(Bm, -1, -1), rdt, Bm)
-        _su4_launch(False, pulses.to(rdt).contiguous(), tgt, err, None, 1, 0, J, (0.0, 0.0), 0, 0, U, None, None, None, None, 0)
+        _su4_launch(False, pulses.to(rdt).contiguous(), tgt, err, None, 1, 0, J, (0.0, 0.0), 0, 0, U, None, None, None, None,
+                    flags)
     return torch.view_as_complex(U)
 
 
