@@ -384,6 +384,19 @@ struct Su4Plan {
     int n_tiles, splits;
     size_t smem;
 };
+// resident blocks per SM of the kernel this plan launches (occupancy API; registers decide: 6 for the FP32
+// eigenframe fwd+bwd kernel).  The grid is sized to ONE wave of resident blocks with equal tile counts.
+template <typename K>
+static int su4_blocks_per_sm(K kern, size_t smem) {
+    int n = 0;
+    if (smem > 48 * 1024) (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kSu4Threads, smem) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}
+
 static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags, bool bwd) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
@@ -391,17 +404,28 @@ static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fla
         sms = 148;
     }
     Su4Plan pl;
+    const bool pade = (flags & UQOC_FLAG_SU4_PADE) != 0, f64 = dtype == UQOC_F64;
+    if (pade) pl.smem = f64 ? su4_smem_bytes<double>((int)L, bwd) : su4_smem_bytes<float>((int)L, bwd);
+    else pl.smem = f64 ? su4e_smem_bytes<double>((int)L, bwd) : su4e_smem_bytes<float>((int)L, bwd);
+    int occ;
+    if (pade) {
+        occ = f64 ? (bwd ? su4_blocks_per_sm(su4_kernel<double, true>, pl.smem) : su4_blocks_per_sm(su4_kernel<double, false>, pl.smem))
+                  : (bwd ? su4_blocks_per_sm(su4_kernel<float, true>, pl.smem) : su4_blocks_per_sm(su4_kernel<float, false>, pl.smem));
+    } else {
+        occ = f64 ? (bwd ? su4_blocks_per_sm(su4e_kernel<double, true>, pl.smem) : su4_blocks_per_sm(su4e_kernel<double, false>, pl.smem))
+                  : (bwd ? su4_blocks_per_sm(su4e_kernel<float, true>, pl.smem) : su4_blocks_per_sm(su4e_kernel<float, false>, pl.smem));
+    }
     pl.n_tiles = (int)((M + kSu4Threads - 1) / kSu4Threads);
-    int64_t splits = ((int64_t)sms * 8 + B - 1) / B;
-    if (splits > pl.n_tiles) splits = pl.n_tiles;
+    // one wave: at most sms*occ blocks; every block of a target walks `rounds` tiles (the last may walk one less)
+    int64_t splits = ((int64_t)sms * occ) / B;
     if (splits < 1) splits = 1;
+    if (splits > pl.n_tiles) splits = pl.n_tiles;
+    const int64_t rounds = (pl.n_tiles + splits - 1) / splits;
+    splits = (pl.n_tiles + rounds - 1) / rounds;
+    if (splits > 4095) splits = 4095;
     const int fsp = (flags >> 18) & 0xFFF;
     if (fsp) splits = fsp < pl.n_tiles ? fsp : pl.n_tiles;
     pl.splits = (int)splits;
-    if (flags & UQOC_FLAG_SU4_PADE)
-        pl.smem = dtype == UQOC_F64 ? su4_smem_bytes<double>((int)L, bwd) : su4_smem_bytes<float>((int)L, bwd);
-    else
-        pl.smem = dtype == UQOC_F64 ? su4e_smem_bytes<double>((int)L, bwd) : su4e_smem_bytes<float>((int)L, bwd);
     return pl;
 }
 

@@ -85,6 +85,8 @@ struct Su4Frame {
     T V[4][4];       // V[i][m]
     T lam[4];        // mu/2 (hi part in FP32)
     T lam_lo[4];     // FP32: mu/2 - float(mu/2);  FP64: 0
+    T dl[3];         // lam[m] - lam[m+1]  (the backward sweep only needs phase DIFFERENCES)
+    T dl_lo[3];
     T te;            // 1 + eps
 };
 
@@ -102,30 +104,69 @@ __device__ __forceinline__ void su4_make_frame(Su4Frame<T>& f, T d1, T d2, T eps
         f.lam[m] = (T)l;
         f.lam_lo[m] = (T)(l - (double)f.lam[m]);
     }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const double l = 0.5 * (mu[m] - mu[m + 1]);
+        f.dl[m] = (T)l;
+        f.dl_lo[m] = (T)(l - (double)f.dl[m]);
+    }
     f.te = (T)1 + eps;
 }
 
-// full-sign sin/cos of the eigenphases.  FP32: the mod-pi polynomial pair of uqoc_common.cuh with the sign
-// (-1)^k restored by an integer XOR (ALU pipe); FP64: libm.
-__device__ __forceinline__ void su4_sincos(float h, float& s, float& c) {
-    int kb;
-    sincos_modpi(h, s, c, kb);
-    const int sg = kb << 31;
-    s = __int_as_float(__float_as_int(s) ^ sg);
-    c = __int_as_float(__float_as_int(c) ^ sg);
+// full-sign sin/cos of the eigenphases from the shared-memory table {sin[1024] | cos[1024]} of (k pi/1024).
+// FP32: first-order residual like the packed SU(2) kernel (angle error <= 1.2e-9; the radial error <= 1.2e-6 has
+// zero mean and is Hermitian to first order, so the Newton-Schulz step on Q_L removes it); 6 FMA-pipe
+// instructions + 2 LDS, the sign (-1)^(k div 1024) restored by an integer XOR.  FP64: SinCos<double, SC_TABLE>.
+__device__ __forceinline__ void su4_sincos(float h, float& s, float& c, const float* __restrict__ tab) {
+    const float MAGIC = 12582912.0f;
+    float kf = fmaf(h, 325.94931f, MAGIC);
+    const int k = __float_as_int(kf);
+    kf -= MAGIC;
+    float r = fmaf(kf, -0.003067961661145091f, h);
+    r = fmaf(kf, 8.537380524753502e-11f, r);
+    const float st = tab[k & 1023], ct = tab[1024 + (k & 1023)];
+    const int sg = (k << 21) & 0x80000000;
+    s = __int_as_float(__float_as_int(fmaf(r, ct, st)) ^ sg);
+    c = __int_as_float(__float_as_int(fmaf(-r, st, ct)) ^ sg);
 }
-__device__ __forceinline__ void su4_sincos(double h, double& s, double& c) { ::sincos(h, &s, &c); }
+__device__ __forceinline__ void su4_sincos(double h, double& s, double& c, const double* __restrict__ tab) {
+    int kb;
+    SinCos<double, SC_TABLE>::eval(h, s, c, kb, tab);
+    if (kb & 1) {
+        s = -s;
+        c = -c;
+    }
+}
 
 template <typename T>
-__device__ __forceinline__ void su4_phases(const Su4Frame<T>& f, T tau, T (&c)[4], T (&s)[4]) {
+__device__ __forceinline__ void su4_phases(const Su4Frame<T>& f, T tau, T (&c)[4], T (&s)[4], const T* __restrict__ tab) {
     const T t = tau * f.te;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         T h;
         if constexpr (sizeof(T) == 4) h = fmaf(f.lam[m], t, f.lam_lo[m] * t);
         else h = f.lam[m] * t;
-        su4_sincos(h, s[m], c[m]);
+        su4_sincos(h, s[m], c[m], tab);
     }
+}
+// w[pair(m,n)] = e^{i(h_m - h_n)}, m < n: three table look-ups (adjacent differences) and three complex products
+template <typename T>
+__device__ __forceinline__ void su4_phase_diffs(const Su4Frame<T>& f, T tau, T (&wr)[6], T (&wi)[6], const T* __restrict__ tab) {
+    const T t = tau * f.te;
+    T c[3], s[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        T h;
+        if constexpr (sizeof(T) == 4) h = fmaf(f.dl[m], t, f.dl_lo[m] * t);
+        else h = f.dl[m] * t;
+        su4_sincos(h, s[m], c[m], tab);
+    }
+    wr[0] = c[0]; wi[0] = s[0];                                   // (0,1)
+    wr[3] = c[1]; wi[3] = s[1];                                   // (1,2)
+    wr[5] = c[2]; wi[5] = s[2];                                   // (2,3)
+    wr[1] = c[0] * c[1] - s[0] * s[1]; wi[1] = c[0] * s[1] + s[0] * c[1];       // (0,2) = (0,1)(1,2)
+    wr[4] = c[1] * c[2] - s[1] * s[2]; wi[4] = c[1] * s[2] + s[1] * c[2];       // (1,3) = (1,2)(2,3)
+    wr[2] = wr[1] * c[2] - wi[1] * s[2]; wi[2] = wr[1] * s[2] + wi[1] * c[2];   // (0,3) = (0,2)(2,3)
 }
 
 // ------------------------------------------------------------------ forward step  Q <- V D V^T G Q
@@ -223,10 +264,11 @@ __device__ __forceinline__ void herm_conj_real(Herm4<T>& E, const Herm4<T>& A, c
 constexpr int kSu4eThreads = 64;
 constexpr int kSu4eWarps = kSu4eThreads / 32;
 
-// shared memory: per pulse {fw[4], tau, b1[4], b2[4]} + target' (32) + last-frame phases (8) + scratch + acc
+// shared memory: sin/cos table (2 x 1024) + per pulse {fw[4], tau, b1[4], b2[4]} + target' (32) + last-frame
+// phases (8) + scratch + acc
 template <typename T>
 __host__ __device__ inline size_t su4e_smem_bytes(int L, bool bwd) {
-    size_t n = (size_t)L * (bwd ? 13 : 5) + 32 + 8 + kSu4eWarps;
+    size_t n = 2048 + (size_t)L * (bwd ? 13 : 5) + 32 + 8 + kSu4eWarps;
     if (bwd) n += (size_t)kSu4eWarps * L * 3;
     return n * sizeof(T) + 16;
 }
@@ -235,7 +277,8 @@ template <typename T, bool BWD>
 __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = p.L;
-    T* fw = reinterpret_cast<T*>(smem_raw);                 // [L][4]  cos a, sin a, cos b, sin b
+    T* tab = reinterpret_cast<T*>(smem_raw);                // {sin[1024] | cos[1024]} of k pi/1024
+    T* fw = tab + 2048;                                     // [L][4]  cos a, sin a, cos b, sin b
     T* b1 = fw + (size_t)L * 4;                             // [L][4]  cos dphi1, sin dphi1, cos dphi2, sin dphi2
     T* b2 = b1 + (BWD ? (size_t)L * 4 : 0);                 // [L][4]  cos(d1+d2), sin(d1+d2), cos(d1-d2), sin(d1-d2)
     T* tauv = b2 + (BWD ? (size_t)L * 4 : 0);               // [L]
@@ -246,6 +289,23 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int split = blockIdx.x % p.splits, b = blockIdx.x / p.splits;
     {
+        // table first: 16 independent loads per thread in flight while the pulse trigonometry runs
+        T tv[2][16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if constexpr (sizeof(T) == 4) {
+                tv[0][u] = g_sin_table[tid + u * kSu4eThreads];
+                tv[1][u] = g_cos_table[tid + u * kSu4eThreads];
+            } else {
+                tv[0][u] = g_sin_table_f64[tid + u * kSu4eThreads];
+                tv[1][u] = g_cos_table_f64[tid + u * kSu4eThreads];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            tab[tid + u * kSu4eThreads] = tv[0][u];
+            tab[1024 + tid + u * kSu4eThreads] = tv[1][u];
+        }
         const T* pb = p.pulses + (size_t)b * L * 3;
         for (int i = tid; i < L; i += kSu4eThreads) {
             const double p1 = (double)pb[3 * i], p2 = (double)pb[3 * i + 1];
@@ -315,7 +375,7 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
             }
         for (int k = 0; k < L; ++k) {
             T c[4], s[4];
-            su4_phases<T>(f, tauv[k], c, s);
+            su4_phases<T>(f, tauv[k], c, s, tab);
             su4e_fwd_step<T>(qr, qi, f, c, s, fw[4 * k], fw[4 * k + 1], fw[4 * k + 2], fw[4 * k + 3]);
         }
         if constexpr (sizeof(T) == 4) {
@@ -416,8 +476,8 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
                 }
             }
             for (int k = L - 1; k >= 0; --k) {
-                T c[4], s[4];
-                su4_phases<T>(f, tauv[k], c, s);
+                T wr[6], wi[6];
+                su4_phase_diffs<T>(f, tauv[k], wr, wi, tab);
                 const T z1a = A.dg[0] + A.dg[1] - A.dg[2] - A.dg[3];
                 const T z2a = A.dg[0] - A.dg[1] + A.dg[2] - A.dg[3];
                 Herm4<T> E;
@@ -425,15 +485,11 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
                 T g_tau = f.te * (E.dg[0] * f.lam[0] + E.dg[1] * f.lam[1] + E.dg[2] * f.lam[2] + E.dg[3] * f.lam[3]);
                 // E'_mn = E_mn e^{i(h_m - h_n)}
 #pragma unroll
-                for (int m = 0; m < 3; ++m)
-#pragma unroll
-                    for (int n = m + 1; n < 4; ++n) {
-                        const T wr = c[m] * c[n] + s[m] * s[n], wi = s[m] * c[n] - c[m] * s[n];
-                        const int pq = su4_pair(m, n);
-                        const T er = E.re[pq], ei = E.im[pq];
-                        E.re[pq] = er * wr - ei * wi;
-                        E.im[pq] = er * wi + ei * wr;
-                    }
+                for (int pq = 0; pq < 6; ++pq) {
+                    const T er = E.re[pq], ei = E.im[pq];
+                    E.re[pq] = er * wr[pq] - ei * wi[pq];
+                    E.im[pq] = er * wi[pq] + ei * wr[pq];
+                }
                 Herm4<T> X;
                 herm_conj_real<T, true>(X, E, f);
                 const T z1b = X.dg[0] + X.dg[1] - X.dg[2] - X.dg[3];
