@@ -227,6 +227,16 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     const bool lead = (WPS == 1) || warp == 0;             // the warp that reports per-sample outputs
 
     {
+        // sin/cos table: all 16 loads of a thread in flight before the pulse trigonometry, stored after it
+        // (a load -> store loop serialises 8 L2 round trips per thread: 4 us of a 55 us launch at BASELINE config 3)
+        float tv[2][kTabN / kThreads];
+        if (SC == SC_TABLE) {
+#pragma unroll
+            for (int u = 0; u < kTabN / kThreads; ++u) {
+                tv[0][u] = g_sin_table[tid + u * kThreads];
+                tv[1][u] = g_cos_table[tid + u * kThreads];
+            }
+        }
         const float* pb = p.pulses + (size_t)b * L * 2;
         for (int i = tid; i < CT; i += kThreads) {
             const int ic = i < L ? i : L - 1;
@@ -247,9 +257,10 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             for (int i = tid; i < kWarps * C * 2; i += kThreads) acc[i] = 0.0f;
         }
         if (SC == SC_TABLE) {
-            for (int i = tid; i < kTabN; i += kThreads) {
-                tsin[i] = g_sin_table[i];
-                tcos[i] = g_cos_table[i];
+#pragma unroll
+            for (int u = 0; u < kTabN / kThreads; ++u) {
+                tsin[tid + u * kThreads] = tv[0][u];
+                tcos[tid + u * kThreads] = tv[1][u];
             }
         }
     }

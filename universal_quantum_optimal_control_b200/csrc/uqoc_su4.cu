@@ -237,7 +237,7 @@ __host__ __device__ inline size_t su4_smem_bytes(int L, bool bwd) {
 
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(kSu4Threads) su4_kernel(const Su4Params<T> p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(32) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);            // [L][5] = cos phi1, sin phi1, cos phi2, sin phi2, tau
     T* tgt = tab + (size_t)p.L * 5;                     // [32]
     T* scratch = tgt + 32;                              // [warps]

@@ -25,6 +25,7 @@
 // Newton-Schulz step (removes, to first order, the norm drift caused by V_f^T V_f = I + O(6e-8)).
 #pragma once
 #include "uqoc_su2_kernels.cuh"
+#include "uqoc_su2_x2.cuh"   // F2 / fma2 / mul2 / f2b packed-FP32 helpers
 
 namespace uqoc {
 
@@ -54,10 +55,15 @@ __device__ __forceinline__ void su4_jacobi(double d1, double d2, double J, doubl
             for (int q = p + 1; q < 4; ++q) {
                 const double apq = A[p][q];
                 if (fabs(apq) > 1e-290) {
-                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                    const double t = copysign(1.0, theta) / (fabs(theta) + ::sqrt(::fma(theta, theta, 1.0)));
-                    const double c = ::rsqrt(::fma(t, t, 1.0));
-                    const double s = t * c;
+                    // rotation by the SMALL angle (|theta| <= pi/4) that zeroes A[p][q], division-free:
+                    // cos 2theta = |d|/r, c^2 = (1 + cos 2theta)/2, s = sign(d) apq / (r c), t = s/c
+                    const double d = A[q][q] - A[p][p];
+                    const double inv_r = ::rsqrt(::fma(d, d, 4.0 * apq * apq));
+                    const double c2 = ::fma(0.5 * fabs(d), inv_r, 0.5);
+                    const double inv_c = ::rsqrt(c2);
+                    const double c = c2 * inv_c;
+                    const double s = copysign(apq, apq * d) * inv_r * inv_c;
+                    const double t = s * inv_c;
                     A[p][p] -= t * apq;
                     A[q][q] += t * apq;
                     A[p][q] = A[q][p] = 0.0;
@@ -204,6 +210,74 @@ __device__ __forceinline__ void su4e_fwd_step(T (&qr)[4][4], T (&qi)[4][4], cons
         }
 }
 
+// FP32 forward step with two COLUMNS of Q per 64-bit register pair (FFMA2): every product has a per-sample or
+// per-pulse scalar on one side, which rides in the 32-bit broadcast operand form, so the 384 FMA-pipe lane
+// operations of a step issue as 192 instructions (the scalar kernel is issue-bound: ncu 80 % issue-active).
+// qr[i][jp], qi[i][jp]: row i, column pair jp = (2jp, 2jp+1).
+__device__ __forceinline__ void su4e_fwd_step_x2(F2 (&qr)[4][2], F2 (&qi)[4][2], const Su4Frame<float>& f, const float (&c)[4],
+                                                 const float (&s)[4], float ca, float sa, float cb, float sb) {
+    // Operand order matters: an FFMA2 that reads two fresh register pairs sustains 76 % of the pipe, one that
+    // reads one fresh pair (the other from the operand-reuse cache, the scalar in the 32-bit broadcast slot)
+    // 95 % (tools/ubench/fma_ubench.cu modes 5 / 6).  So every product below is written "outer-product" style:
+    // four consecutive instructions share the SAME packed multiplicand and update four different accumulators.
+    const F2 Ca = f2b(ca), Sa = f2b(sa), Cb = f2b(cb), Sb = f2b(sb);
+    F2 xr[4][2], xi[4][2];
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const F2 Cg = (i == 0 || i == 3) ? Ca : Cb;
+            const F2 Sg = (i == 0) ? Sa : (i == 1) ? Sb : (i == 2) ? neg2(Sb) : neg2(Sa);   // e^{+i..} rows 0,1; e^{-i..} rows 2,3
+            const F2 t1 = mul2(Cg, qr[i][jp]), t2 = mul2(Sg, qr[i][jp]);
+            xr[i][jp] = fma2(neg2(Sg), qi[i][jp], t1);
+            xi[i][jp] = fma2(Cg, qi[i][jp], t2);
+        }
+    }
+    // Y = V^T X
+    F2 ar[4][2], ai[4][2];
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ar[m][jp] = mul2(f2b(f.V[0][m]), xr[0][jp]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ai[m][jp] = mul2(f2b(f.V[0][m]), xi[0][jp]);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ar[m][jp] = fma2(f2b(f.V[i][m]), xr[i][jp], ar[m][jp]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ai[m][jp] = fma2(f2b(f.V[i][m]), xi[i][jp], ai[m][jp]);
+        }
+    }
+    // D Y (row m times c_m - i s_m)
+    F2 yr[4][2], yi[4][2];
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const F2 cm = f2b(c[m]), sm = f2b(s[m]);
+            const F2 t1 = mul2(cm, ar[m][jp]), t2 = mul2(neg2(sm), ar[m][jp]);
+            yr[m][jp] = fma2(sm, ai[m][jp], t1);
+            yi[m][jp] = fma2(cm, ai[m][jp], t2);
+        }
+    }
+    // Q = V Y
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qr[i][jp] = mul2(f2b(f.V[i][0]), yr[0][jp]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qi[i][jp] = mul2(f2b(f.V[i][0]), yi[0][jp]);
+#pragma unroll
+        for (int m = 1; m < 4; ++m) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qr[i][jp] = fma2(f2b(f.V[i][m]), yr[m][jp], qr[i][jp]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qi[i][jp] = fma2(f2b(f.V[i][m]), yi[m][jp], qi[i][jp]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ Hermitian 4x4 in packed form
 // A = S + iK, S symmetric (dg + re), K antisymmetric (im, upper triangle).  Pair index of (i<j):
 // (0,1)=0 (0,2)=1 (0,3)=2 (1,2)=3 (1,3)=4 (2,3)=5.
@@ -275,7 +349,7 @@ __host__ __device__ inline size_t su4e_smem_bytes(int L, bool bwd) {
 
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(32) unsigned char smem_raw[];
     const int L = p.L;
     T* tab = reinterpret_cast<T*>(smem_raw);                // {sin[1024] | cos[1024]} of k pi/1024
     T* fw = tab + 2048;                                     // [L][4]  cos a, sin a, cos b, sin b
@@ -373,10 +447,33 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
                 qr[i][jj] = (i == jj) ? (T)1 : (T)0;
                 qi[i][jj] = (T)0;
             }
-        for (int k = 0; k < L; ++k) {
-            T c[4], s[4];
-            su4_phases<T>(f, tauv[k], c, s, tab);
-            su4e_fwd_step<T>(qr, qi, f, c, s, fw[4 * k], fw[4 * k + 1], fw[4 * k + 2], fw[4 * k + 3]);
+        if constexpr (sizeof(T) == 4) {
+            F2 pr[4][2], pi[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    pr[i][jp] = f2(qr[i][2 * jp], qr[i][2 * jp + 1]);
+                    pi[i][jp] = f2b(0.0f);
+                }
+            for (int k = 0; k < L; ++k) {
+                float c[4], s[4];
+                su4_phases<float>(f, tauv[k], c, s, tab);
+                su4e_fwd_step_x2(pr, pi, f, c, s, fw[4 * k], fw[4 * k + 1], fw[4 * k + 2], fw[4 * k + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    qr[i][2 * jp] = f2lo(pr[i][jp]); qr[i][2 * jp + 1] = f2hi(pr[i][jp]);
+                    qi[i][2 * jp] = f2lo(pi[i][jp]); qi[i][2 * jp + 1] = f2hi(pi[i][jp]);
+                }
+        } else {
+            for (int k = 0; k < L; ++k) {
+                T c[4], s[4];
+                su4_phases<T>(f, tauv[k], c, s, tab);
+                su4e_fwd_step<T>(qr, qi, f, c, s, fw[4 * k], fw[4 * k + 1], fw[4 * k + 2], fw[4 * k + 3]);
+            }
         }
         if constexpr (sizeof(T) == 4) {
             // one Newton-Schulz step  Q <- Q (3I - Q^dagger Q)/2
