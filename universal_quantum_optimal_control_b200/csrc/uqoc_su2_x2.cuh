@@ -103,10 +103,14 @@ __device__ __forceinline__ void sincos2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_
 // final re-normalisation of P_L) and has zero mean because the table is pre-scaled by 1 - (pi/2N)^2/6.
 // 6 FMA-pipe instructions (4 with immediates) instead of 14; the sign (-1)^(k div N) is dropped like in
 // the polynomial path (kb returns k >> 10 so the U_out kernel can track it).
-template <int NP, int SC>
+// FULL: index the full-period table (k mod 2N): the signs of (s, c) are then exact and kb = 0 (the backward
+// sweep looks up the DOUBLE angle 2h this way: cos 2h / sin 2h are what the adjoint rotation needs, and taking
+// them from the table instead of the double-angle identities saves 3 FMA-pipe instructions per pair-step).
+template <int NP, int SC, bool FULL = false>
 __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
                                           const float* __restrict__ tsin, const float* __restrict__ tcos) {
     if constexpr (SC == SC_TABLE) {
+        constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
         const float MAGIC = 12582912.0f;
         F2 kf[NP], r[NP], st[NP], ct[NP];
 #pragma unroll
@@ -114,9 +118,9 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
             const int k0 = __float_as_int(f2lo(kf[u])), k1 = __float_as_int(f2hi(kf[u]));
-            kb[2 * u] = k0 >> 10;
-            kb[2 * u + 1] = k1 >> 10;
-            const int i0 = k0 & (kTabN - 1), i1 = k1 & (kTabN - 1);
+            kb[2 * u] = FULL ? 0 : (k0 >> 10);
+            kb[2 * u + 1] = FULL ? 0 : (k1 >> 10);
+            const int i0 = k0 & MASK, i1 = k1 & MASK;
             st[u] = f2(tsin[i0], tsin[i1]);
             ct[u] = f2(tcos[i0], tcos[i1]);
         }
@@ -184,7 +188,7 @@ __host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool
     if (bwd) bytes += rows * 16;                                  // {cos dphi, sin dphi, tau, -} rows
     if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);     // gradient accumulators (per warp / per chunk)
     bytes += 32 * sizeof(float);
-    if (table) bytes += 2 * (size_t)UQOC_SINCOS_TABLE_N * sizeof(float);
+    if (table) bytes += 2 * (size_t)(bwd ? UQOC_SINCOS_TABLE_LEN : UQOC_SINCOS_TABLE_N) * sizeof(float);   // bwd: full period
     if (wps > 1) bytes += (size_t)kWarps * st * 5 * 32 * sizeof(float);   // chunk-product (+ parity) exchange
     return bytes;
 }
@@ -212,9 +216,10 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     float4* bwd4 = fwd4 + CT;
     float* acc = reinterpret_cast<float*>(bwd4 + (BWD ? CT : 0));
     float* scratch = acc + (BWD ? (size_t)kWarps * C * 2 : 0);
+    constexpr int TLEN = (SC == SC_TABLE) ? (BWD ? UQOC_SINCOS_TABLE_LEN : kTabN) : 0;   // table entries staged
     float* tsin = scratch + 32;
-    float* tcos = tsin + kTabN;
-    float* xq = tcos + (SC == SC_TABLE ? kTabN : -kTabN);   // [kWarps][ST][5][32], WPS > 1 only
+    float* tcos = tsin + TLEN;
+    float* xq = tcos + TLEN;                                // [kWarps][ST][5][32], WPS > 1 only
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -229,10 +234,10 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     {
         // sin/cos table: all 16 loads of a thread in flight before the pulse trigonometry, stored after it
         // (a load -> store loop serialises 8 L2 round trips per thread: 4 us of a 55 us launch at BASELINE config 3)
-        float tv[2][kTabN / kThreads];
+        float tv[2][(TLEN > 0 ? TLEN : kThreads) / kThreads];
         if (SC == SC_TABLE) {
 #pragma unroll
-            for (int u = 0; u < kTabN / kThreads; ++u) {
+            for (int u = 0; u < TLEN / kThreads; ++u) {
                 tv[0][u] = g_sin_table[tid + u * kThreads];
                 tv[1][u] = g_cos_table[tid + u * kThreads];
             }
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
         }
         if (SC == SC_TABLE) {
 #pragma unroll
-            for (int u = 0; u < kTabN / kThreads; ++u) {
+            for (int u = 0; u < TLEN / kThreads; ++u) {
                 tsin[tid + u * kThreads] = tv[0][u];
                 tcos[tid + u * kThreads] = tv[1][u];
             }
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
 
     for (int tile = split; tile < p.n_tiles; tile += p.splits) {
         // ---- per-sample constants, packed pairwise: pair u = samples (2u, 2u+1) of this thread
-        F2 ka[NP], kr[NP], kr2[NP], kdl[NP], kae[NP];
+        F2 ka[NP], ka2[NP], kr[NP], kr2[NP], kdl[NP], kae[NP];
         bool valid[ST];
         size_t sidx[ST];
         {
@@ -300,6 +305,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
 #pragma unroll
             for (int u = 0; u < NP; ++u) {
                 ka[u] = f2(kc[2 * u].a, kc[2 * u + 1].a);
+                ka2[u] = f2(kc[2 * u].a2, kc[2 * u + 1].a2);
                 kr[u] = f2(kc[2 * u].r, kc[2 * u + 1].r);
                 kr2[u] = f2(kc[2 * u].r2, kc[2 * u + 1].r2);
                 kdl[u] = f2(kc[2 * u].delta, kc[2 * u + 1].delta);
@@ -467,20 +473,37 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                     F2 gp = f2b(0.0f), gt = f2b(0.0f);
                     F2 h[NP], s[NP], c[NP], s2[NP], C2[NP], Sr[NP], k1_[NP], t[NP], uu[NP], K[NP], BS[NP], A1[NP], B1[NP], Wz[NP];
                     int kb[ST];
+                    if constexpr (SC == SC_TABLE) {
+                        // (sin 2h, cos 2h) straight from the full-period table
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
-                    sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
+                        for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka2[u]);
+                        sincos2_n<NP, SC, true>(h, s2, C2, kb, tsin, tcos);
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        s2[u] = add2(s[u], s[u]);
-                        t[u] = fma2(kdl[u], W3[u], A[u]);
-                        uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
-                    }
+                        for (int u = 0; u < NP; ++u) {
+                            t[u] = fma2(kdl[u], W3[u], A[u]);
+                            uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                        }
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        C2[u] = fma2(neg2(s2[u]), s[u], one);
-                        Sr[u] = mul2(mul2(s2[u], kr[u]), c[u]);
-                        gt = fma2(kae[u], t[u], gt);
+                        for (int u = 0; u < NP; ++u) {
+                            Sr[u] = mul2(s2[u], kr[u]);
+                            gt = fma2(kae[u], t[u], gt);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
+                        sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) {
+                            s2[u] = add2(s[u], s[u]);
+                            t[u] = fma2(kdl[u], W3[u], A[u]);
+                            uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                        }
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) {
+                            C2[u] = fma2(neg2(s2[u]), s[u], one);
+                            Sr[u] = mul2(mul2(s2[u], kr[u]), c[u]);
+                            gt = fma2(kae[u], t[u], gt);
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < NP; ++u) {
