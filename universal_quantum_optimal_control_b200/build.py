@@ -39,7 +39,7 @@ def _stamp() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".inc")):
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(f.encode())
                     h.update(fh.read())

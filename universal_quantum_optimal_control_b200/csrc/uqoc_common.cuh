@@ -234,6 +234,8 @@ struct SampleConst {
     T r2;     // 1/w^2
     T delta;  // detuning
     T ae;     // (1+eps)/2 = a*r : d h / d tau projected on the axis
+    T ap;     // a  * 1024/pi : table index of the half angle per unit tau (packed table kernel)
+    T a2p;    // a2 * 1024/pi : table index of the full angle per unit tau
 };
 template <typename T>
 __device__ __forceinline__ SampleConst<T> make_sample_const(T delta, T eps) {
@@ -249,6 +251,8 @@ __device__ __forceinline__ SampleConst<T> make_sample_const(T delta, T eps) {
     k.r2 = (T)(r * r);
     k.delta = delta;
     k.ae = (T)(0.5 * (1.0 + e));
+    k.ap = (T)(0.5 * (1.0 + e) * w * 325.94932345220167);
+    k.a2p = (T)((1.0 + e) * w * 325.94932345220167);
     return k;
 }
 

@@ -181,6 +181,41 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
     }
 }
 
+// Table sin/cos of tau * a for NP pairs, from the per-sample table-index slope kap = a * N/pi:
+//   kf = fma(tau, kap, MAGIC)  (k in the low mantissa bits),  frac = fma(tau, kap, -(kf - MAGIC))  (one rounding),
+//   r = frac * pi/N,  (s, c) = (st + r ct, ct - r st).
+// 6 FMA-pipe instructions; the angle tau*a itself is never formed (the Cody-Waite pair of sincos2_n's table
+// path is replaced by the exact FMA residual).  FULL as in sincos2_n.
+template <int NP, bool FULL>
+__device__ __forceinline__ void sincos2_tab(F2 tau, const F2 (&kap)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
+                                            const float* __restrict__ tsin, const float* __restrict__ tcos) {
+    constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
+    const float MAGIC = 12582912.0f;
+    F2 kf[NP], fr[NP], st[NP], ct[NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) kf[u] = fma2(tau, kap[u], f2b(MAGIC));
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+        const int k0 = __float_as_int(f2lo(kf[u])), k1 = __float_as_int(f2hi(kf[u]));
+        kb[2 * u] = FULL ? 0 : (k0 >> 10);
+        kb[2 * u + 1] = FULL ? 0 : (k1 >> 10);
+        const int i0 = k0 & MASK, i1 = k1 & MASK;
+        st[u] = f2(tsin[i0], tsin[i1]);
+        ct[u] = f2(tcos[i0], tcos[i1]);
+    }
+#pragma unroll
+    for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
+#pragma unroll
+    for (int u = 0; u < NP; ++u) fr[u] = fma2(tau, kap[u], kf[u]);
+#pragma unroll
+    for (int u = 0; u < NP; ++u) fr[u] = mul2(fr[u], f2b(0.0030679615757712823f));
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+        s[u] = fma2(fr[u], ct[u], st[u]);
+        c[u] = fma2(neg2(fr[u]), st[u], ct[u]);
+    }
+}
+
 // shared memory of one block of the packed kernel (bytes).  C = pulses per chunk, WPS chunks.
 __host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool bwd, bool table) {
     const size_t rows = (size_t)C * wps;
@@ -282,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
 
     for (int tile = split; tile < p.n_tiles; tile += p.splits) {
         // ---- per-sample constants, packed pairwise: pair u = samples (2u, 2u+1) of this thread
-        F2 ka[NP], ka2[NP], kr[NP], kr2[NP], kdl[NP], kae[NP];
+        F2 ka[NP], ka2[NP], kr[NP], kr2[NP], kdl[NP], kae[NP];   // ka / ka2: table-index slopes when SC == SC_TABLE
         bool valid[ST];
         size_t sidx[ST];
         {
@@ -304,8 +339,13 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             }
 #pragma unroll
             for (int u = 0; u < NP; ++u) {
-                ka[u] = f2(kc[2 * u].a, kc[2 * u + 1].a);
-                ka2[u] = f2(kc[2 * u].a2, kc[2 * u + 1].a2);
+                if (SC == SC_TABLE) {
+                    ka[u] = f2(kc[2 * u].ap, kc[2 * u + 1].ap);
+                    ka2[u] = f2(kc[2 * u].a2p, kc[2 * u + 1].a2p);
+                } else {
+                    ka[u] = f2(kc[2 * u].a, kc[2 * u + 1].a);
+                    ka2[u] = f2(kc[2 * u].a2, kc[2 * u + 1].a2);
+                }
                 kr[u] = f2(kc[2 * u].r, kc[2 * u + 1].r);
                 kr2[u] = f2(kc[2 * u].r2, kc[2 * u + 1].r2);
                 kdl[u] = f2(kc[2 * u].delta, kc[2 * u + 1].delta);
@@ -330,9 +370,13 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             const F2 cc = f2b(row.x), ss = f2b(row.y), tau = f2b(row.z);
             F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP], na[NP], nb[NP], nc[NP], nd[NP];
             int kb[ST];
+            if constexpr (SC == SC_TABLE) {
+                sincos2_tab<NP, false>(tau, ka, s, c, kb, tsin, tcos);
+            } else {
 #pragma unroll
-            for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
-            sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
+                for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
+                sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
+            }
             if ((SC == SC_POLY || SC == SC_TABLE) && !BWD) {
 #pragma unroll
                 for (int u = 0; u < ST; ++u) par[u] ^= kb[u];
@@ -475,9 +519,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                     int kb[ST];
                     if constexpr (SC == SC_TABLE) {
                         // (sin 2h, cos 2h) straight from the full-period table
-#pragma unroll
-                        for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka2[u]);
-                        sincos2_n<NP, SC, true>(h, s2, C2, kb, tsin, tcos);
+                        sincos2_tab<NP, true>(tau, ka2, s2, C2, kb, tsin, tcos);
 #pragma unroll
                         for (int u = 0; u < NP; ++u) {
                             t[u] = fma2(kdl[u], W3[u], A[u]);
