@@ -55,8 +55,16 @@ __device__ __forceinline__ F2 sub2(F2 a, F2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
     return d;
 }
-// ptxas folds this into the consumer's operand-negate modifier (no instruction is emitted)
+// ptxas folds these into the consumer's operand modifiers (no instruction is emitted): an FFMA2 / FMUL2 source takes
+// a whole-pair negate, a half swap (.LO_HI) and -- in the FIRST source slot only -- a per-half sign pattern (.NP)
+// for free.  So the sign-pattern forms must be passed as the first operand of fma2 / mul2; in the second slot
+// ptxas materialises them (FADD + MOV).
 __device__ __forceinline__ F2 neg2(F2 a) { return f2(-f2lo(a), -f2hi(a)); }
+__device__ __forceinline__ F2 swp2(F2 a) { return f2(f2hi(a), f2lo(a)); }        // (hi, lo)
+__device__ __forceinline__ F2 swp2_np(F2 a) { return f2(-f2hi(a), f2lo(a)); }    // (-hi, lo)
+__device__ __forceinline__ F2 swp2_nn(F2 a) { return f2(-f2hi(a), -f2lo(a)); }   // (-hi, -lo)
+__device__ __forceinline__ F2 sgn2_np(F2 a) { return f2(-f2lo(a), f2hi(a)); }    // (-lo, hi)
+__device__ __forceinline__ F2 sgn2_pn(F2 a) { return f2(f2lo(a), -f2hi(a)); }    // (lo, -hi)
 
 // packed twin of sincos_modpi (uqoc_common.cuh): (s, c) = (-1)^k (sin h, cos h), k in kb_*.
 __device__ __forceinline__ void sincos_modpi2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_hi) {
@@ -354,13 +362,18 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
         }
 
         // ---------------- forward sweep over this warp's chunk ----------------
-        F2 Pa[NP], Pb[NP], Pc[NP], Pd[NP];
+        // The per-pulse scalars (sin/cos, q) are computed with two SAMPLES per register pair; the running product
+        // keeps two COMPONENTS of one sample per pair, X = (a, b), Y = (c, d), so that every Hamilton-product
+        // instruction is  acc += {X | Y with a free swap / sign modifier} * scalar: the per-sample scalar rides in
+        // the 32-bit broadcast slot and X / Y come from the operand-reuse cache -- one fresh 64-bit register read
+        // per FFMA2 instead of two (tools/ubench/fma_ubench.cu: 95 % vs 76 % of the pipe).
+        F2 X[ST], Y[ST];
         int par[ST];
 #pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            Pa[u] = f2b(1.0f);
-            Pb[u] = Pc[u] = Pd[u] = f2b(0.0f);
-            par[2 * u] = par[2 * u + 1] = 0;
+        for (int u = 0; u < ST; ++u) {
+            X[u] = f2(1.0f, 0.0f);
+            Y[u] = f2b(0.0f);
+            par[u] = 0;
         }
 #pragma unroll 2
         for (int jj = 0; jj < C; ++jj) {
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             // which costs no 64-bit register-file read (tools/ubench/fma_ubench.cu modes 5/6)
             const float4 row = fwd4[rb + jj];
             const F2 cc = f2b(row.x), ss = f2b(row.y), tau = f2b(row.z);
-            F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP], na[NP], nb[NP], nc[NP], nd[NP];
+            F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP];
             int kb[ST];
             if constexpr (SC == SC_TABLE) {
                 sincos2_tab<NP, false>(tau, ka, s, c, kb, tsin, tcos);
@@ -390,35 +403,32 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                 q3[u] = mul2(sp[u], kdl[u]);
             }
 #pragma unroll
-            for (int u = 0; u < NP; ++u) {
-                na[u] = mul2(c[u], Pa[u]); nb[u] = mul2(c[u], Pb[u]); nc[u] = mul2(c[u], Pc[u]); nd[u] = mul2(c[u], Pd[u]);
+            for (int v = 0; v < ST; ++v) {
+                const int u = v >> 1;
+                const F2 cs = f2b((v & 1) ? f2hi(c[u]) : f2lo(c[u]));
+                const F2 a1 = f2b((v & 1) ? f2hi(q1[u]) : f2lo(q1[u]));
+                const F2 a2 = f2b((v & 1) ? f2hi(q2[u]) : f2lo(q2[u]));
+                const F2 a3 = f2b((v & 1) ? f2hi(q3[u]) : f2lo(q3[u]));
+                // (na, nb) = c (a, b) + q1 (-b, a) + q2 (-c, d) + q3 (-d, -c)
+                // (nc, nd) = c (c, d) + q1 (-d, c) + q2 (a, -b) + q3 (b, a)
+                F2 nX = mul2(X[v], cs);
+                F2 nY = mul2(Y[v], cs);
+                nX = fma2(swp2_np(X[v]), a1, nX);
+                nY = fma2(sgn2_pn(X[v]), a2, nY);
+                nY = fma2(swp2(X[v]), a3, nY);
+                nY = fma2(swp2_np(Y[v]), a1, nY);
+                nX = fma2(sgn2_np(Y[v]), a2, nX);
+                nX = fma2(swp2_nn(Y[v]), a3, nX);
+                X[v] = nX;
+                Y[v] = nY;
             }
-#pragma unroll
-            for (int u = 0; u < NP; ++u) {
-                na[u] = fma2(neg2(q1[u]), Pb[u], na[u]); nb[u] = fma2(q1[u], Pa[u], nb[u]);
-                nc[u] = fma2(neg2(q1[u]), Pd[u], nc[u]); nd[u] = fma2(q1[u], Pc[u], nd[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < NP; ++u) {
-                na[u] = fma2(neg2(q2[u]), Pc[u], na[u]); nb[u] = fma2(q2[u], Pd[u], nb[u]);
-                nc[u] = fma2(q2[u], Pa[u], nc[u]);       nd[u] = fma2(neg2(q2[u]), Pb[u], nd[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < NP; ++u) {
-                na[u] = fma2(neg2(q3[u]), Pd[u], na[u]); nb[u] = fma2(neg2(q3[u]), Pc[u], nb[u]);
-                nc[u] = fma2(q3[u], Pb[u], nc[u]);       nd[u] = fma2(q3[u], Pa[u], nd[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < NP; ++u) { Pa[u] = na[u]; Pb[u] = nb[u]; Pc[u] = nc[u]; Pd[u] = nd[u]; }
         }
 
         // ---------------- chunk products -> prefix at this chunk's end and the full product ----------------
         Quat<float> PL[ST], Pin[ST];
 #pragma unroll
         for (int u = 0; u < ST; ++u) {
-            const int pu = u >> 1;
-            Pin[u] = (u & 1) ? Quat<float>{f2hi(Pa[pu]), f2hi(Pb[pu]), f2hi(Pc[pu]), f2hi(Pd[pu])}
-                             : Quat<float>{f2lo(Pa[pu]), f2lo(Pb[pu]), f2lo(Pc[pu]), f2lo(Pd[pu])};
+            Pin[u] = Quat<float>{f2lo(X[u]), f2hi(X[u]), f2lo(Y[u]), f2hi(Y[u])};
             PL[u] = Pin[u];
         }
         if constexpr (WPS > 1) {
