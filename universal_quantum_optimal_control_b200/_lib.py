@@ -7,7 +7,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libuqoc.so")
+# UQOC_LIB: load another build of the same ABI (kernel-tuning experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("UQOC_LIB") or os.path.join(HERE, "lib", "libuqoc.so")
 
 F32, F64 = 0, 1
 FLAG_FAST_SINCOS = 1

@@ -236,8 +236,16 @@ __host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool
     return bytes;
 }
 
-// resident-block hint: the table kernel has LDS latency to hide, 6 blocks/SM (<= 80 registers) measured best
-constexpr int x2_min_blocks(int NP, int SC, int WPS) { return (WPS == 4 && NP == 1) ? 7 : ((SC == SC_TABLE) ? 6 : 1); }
+// resident-block hint of the table kernel: 5 blocks/SM (<= 96 registers) measured best (8.33 ms vs 8.50 at 6, 8.37 at 7,
+// 8.58 at 4 on the 4096 x 4096 x 256 launch); tools/variants.sh builds such variants side by side
+#ifndef UQOC_X2_MINB
+#define UQOC_X2_MINB 5
+#endif
+#ifndef UQOC_X2_FWD_UNROLL
+#define UQOC_X2_FWD_UNROLL 2
+#endif
+constexpr int kX2FwdUnroll = UQOC_X2_FWD_UNROLL;
+constexpr int x2_min_blocks(int NP, int SC, int WPS) { return (WPS == 4 && NP == 1) ? 7 : ((SC == SC_TABLE) ? UQOC_X2_MINB : 1); }
 
 // NP  = sample PAIRS per thread (1 or 2)
 // WPS = warps per sample group.  1: every warp owns its own 32*ST samples and the whole pulse train.
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             Y[u] = f2b(0.0f);
             par[u] = 0;
         }
-#pragma unroll 2
+#pragma unroll kX2FwdUnroll
         for (int jj = 0; jj < C; ++jj) {
             // per-pulse values are warp-uniform: f2b() lets ptxas use the 32-bit broadcast operand form (R.F32),
             // which costs no 64-bit register-file read (tools/ubench/fma_ubench.cu modes 5/6)
