@@ -125,6 +125,34 @@ def test_every_launch_shape_matches_oracle(st, lps, nopk, wps, dtype):
         assert abs(val - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
 
 
+@pytest.mark.parametrize("st,lps,nopk,wps,notab", [(2, 1, False, 1, False), (4, 1, False, 1, False), (2, 1, False, 4, False),
+                                                   (4, 1, False, 1, True), (2, 1, True, 0, False), (1, 4, False, 0, False)])
+def test_wide_angle_range_negative_and_multi_turn(st, lps, nopk, wps, notab):
+    """Durations outside the model's range: negative tau (demo L=400 config, tau in [-0.5, 0.5]) and rotations of
+    several turns, strong detuning.  Exercises the table index for negative / wrapped k in the forward (half
+    angle, mod pi) and backward (full angle, mod 2 pi) sweeps, the sign tracking of U_out, and the polynomial /
+    scalar kernels' range reduction."""
+    rng = np.random.default_rng(77)
+    B, L, M = 2, 29, 200
+    pulses = np.stack([rng.uniform(-7.0, 7.0, (B, L)), rng.uniform(-2.0, 6.0, (B, L))], -1).astype(np.float32)
+    pulses[0, 3, 1] = 0.0                                   # a zero-duration pulse is the identity
+    T = rng.normal(size=(B, 2, 2)) + 1j * rng.normal(size=(B, 2, 2))
+    err = np.stack([rng.normal(0, 3.0, B * M), rng.normal(0, 0.1, B * M)]).astype(np.float32)
+    want_l, want_g, want_F = orc.loss_and_grad(pulses.astype(np.float64), T, err.astype(np.float64), M, "infidelity")
+    flags = uq.tuning_flags(st=st, lps=lps, no_packed=nopk, wps=wps, no_table=notab)
+    val, grad, F, _ = _fused(pulses, T, err, M, torch.float32, loss="infidelity", flags=flags)
+    # angles reach ~60 rad here: the FP32 rounding of h itself (6e-8 relative) is 4e-6 rad per pulse
+    assert np.abs(F - want_F).max() < 1e-4
+    assert _relerr(grad, want_g) < 5e-4
+    val64, grad64, F64, _ = _fused(pulses, T, err, M, torch.float64, loss="infidelity", flags=uq.tuning_flags(st=min(st, 2), lps=lps))
+    assert np.abs(F64 - want_F).max() < 1e-11
+    assert _relerr(grad64, want_g) < 1e-10
+    # forward-only U_out keeps the overall sign of the product
+    U = uq.batched_unitary_generator(_t(pulses[0:1]).expand(M, -1, -1), _t(err[:, :M]))
+    want_U = orc.batched_unitary_generator(np.repeat(pulses[0:1].astype(np.float64), M, 0), err[:, :M].astype(np.float64))
+    assert np.abs(U.cpu().numpy() - want_U).max() < 2e-4
+
+
 @pytest.mark.parametrize("st,lps,nopk,wps", SHAPES)
 def test_forward_only_U_out_every_shape(st, lps, nopk, wps):
     rng = np.random.default_rng(5)
