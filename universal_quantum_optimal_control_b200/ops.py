@@ -30,7 +30,7 @@ __all__ = [
     "sharp_loss", "negative_log_loss", "infidelity_loss", "custom_loss",
     "get_ore_ple_error_distribution", "get_ore_error_distribution", "philox_errors",
     "target_coeffs", "tuning_flags", "fp32_peak_tflops",
-    "fused_propagate_loss_su4", "su4_unitary_generator", "philox_errors_su4",
+    "fused_propagate_loss_su4", "su4_unitary_generator", "philox_errors_su4", "autotune_flags",
 ]
 
 
@@ -80,6 +80,48 @@ def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool =
             | (16 if wps == 4 else 0) | (32 if wps == 1 else 0) | (64 if su4_pade else 0)
             | ((st & 0xF) << 8) | ((lps & 0x3F) << 12)
             | ((splits & 0xFFF) << 18))
+
+
+_AUTOTUNE_CACHE: dict = {}
+
+
+def autotune_flags(B: int, L: int, M: int, dtype: torch.dtype = torch.float32, device="cuda", iters: int = 5,
+                   candidates: Optional[Sequence[int]] = None) -> int:
+    """Measure the launch shapes of the fused SU(2) kernel on THIS device for one problem size and return the
+    fastest ``flags`` word (cached per (B, L, M, dtype, device)).  A training loop calls the same shape every
+    step (``trainer.py:80-90``), so one measurement at start-up replaces the library heuristic
+    (``make_plan`` in csrc/uqoc_api.cu), which is tuned on a handful of shapes only.  Synchronises."""
+    dev = torch.device(device)
+    key = (int(B), int(L), int(M), dtype, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key in _AUTOTUNE_CACHE:
+        return _AUTOTUNE_CACHE[key]
+    if candidates is None:
+        candidates = [0] if dtype == torch.float64 else [
+            0, tuning_flags(st=4, wps=1), tuning_flags(st=2, wps=1), tuning_flags(st=4, wps=4), tuning_flags(st=2, wps=4)]
+    g = torch.Generator().manual_seed(0)
+    pulses = torch.stack([(torch.rand(B, L, generator=g) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(B, L, generator=g)], -1).to(dev, dtype)
+    tc = torch.zeros(B, 8, dtype=dtype, device=dev)
+    tc[:, 0] = 2.0                                           # identity target
+    Fsum = torch.empty(B, dtype=dtype, device=dev)
+    G = torch.empty(B, L, 2, dtype=dtype, device=dev)
+    best, best_ms = 0, float("inf")
+    for fl in candidates:
+        try:
+            for i in range(2):
+                _launch_fwdbwd(pulses, tc, None, None, M, 0, (1.0, 0.05), 1, i, None, None, Fsum, G, fl)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                _launch_fwdbwd(pulses, tc, None, None, M, 0, (1.0, 0.05), 1, i, None, None, Fsum, G, fl)
+            e1.record()
+            e1.synchronize()
+        except Exception:                                    # a shape this size does not support (shared memory)
+            continue
+        ms = e0.elapsed_time(e1) / iters
+        if ms < best_ms * 0.98:                              # prefer the earlier (default-first) candidate on ties
+            best, best_ms = fl, ms
+    _AUTOTUNE_CACHE[key] = best
+    return best
 
 
 def target_coeffs(U_target: torch.Tensor, real_dtype: torch.dtype) -> torch.Tensor:

@@ -50,6 +50,7 @@ class FusedStepMixin:
     fused_seed: int = 0
     fused_group = None
     fused_dtype: Optional[torch.dtype] = None
+    fused_autotune: bool = False                 # measure the launch shape once per (B, L, M) (ops.autotune_flags)
     _fused_step: int = 0
     clip_norm: float = 1.0                       # trainer.py:91
 
@@ -66,8 +67,12 @@ class FusedStepMixin:
         if not isinstance(spec, SigmaSpec):               # a reference-style sampler closure: explicit errors
             error = spec(self.monte_carlo * U_target.shape[0]).to(pulses.device)
         self._fused_step += 1
+        kw = {}
+        if self.fused_autotune and pulses.shape[-1] == 2 and self.fused_group is None:
+            kw["flags"] = ops.autotune_flags(pulses.shape[0], pulses.shape[1], self.monte_carlo,
+                                             self.fused_dtype or torch.float32, pulses.device)
         return fn(pulses, U_target, error=error, monte_carlo=self.monte_carlo, sigma=sigma, seed=self.fused_seed,
-                  offset=self._fused_step, loss=loss, dtype=self.fused_dtype, group=self.fused_group)
+                  offset=self._fused_step, loss=loss, dtype=self.fused_dtype, group=self.fused_group, **kw)
 
     def train_epoch(self, U_emb_batch, U_target_batch, error_distribution) -> float:   # trainer.py:58-94
         self.model.train()
