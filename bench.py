@@ -467,6 +467,16 @@ def other_configs(uq, ops, dev):
                                                                            "note": "torch.linalg.matrix_exp + bmm tree + autograd, complex64, cuda"}
     except Exception as e:  # informative only
         out["reference_op_sequence_on_this_B200_B1_L256_M16384_fwdbwd"] = {"error": repr(e)[:200]}
+    # the reference scripts' own step shapes (monte_carlo = 1000, trainer.py:34): shipped single-qubit config
+    # (SCORE.py:316-328 batch 200, L = 100) and the GRAPE script (grape_train.py:306 batch 100, L = 400)
+    for name, (Bs, Ls, Ms, tlo, thi) in (("shipped_score_B200_L100_M1000_fwdbwd", (200, 100, 1000, 0.1, 0.5)),
+                                         ("shipped_grape_B100_L400_M1000_fwdbwd", (100, 400, 1000, 0.035, 0.07))):
+        ps = torch.stack([(torch.rand(Bs, Ls, generator=g) * 2 - 1) * 3.15, tlo + (thi - tlo) * torch.rand(Bs, Ls, generator=g)], -1).to(dev)
+        tcs = uq.target_coeffs(torch.eye(2, dtype=torch.complex64, device=dev)[None].expand(Bs, -1, -1).contiguous(), torch.float32)
+        bufs = torch.empty(Bs + Bs * Ls * 2, device=dev)
+        ms = timed(lambda: (ops._launch_fwdbwd(ps, tcs, None, None, Ms, 0, (1.0, 0.05), 1, 0, None, None, bufs[:Bs], bufs[Bs:], 0),
+                            ops._finalize(bufs[:Bs], Bs * Ms, "sharp", 0.99, 100, bufs[Bs:])))
+        out[name] = {"prop_per_s": Bs * Ms * Ls / (ms * 1e-3), "ms": ms}
     wl = make_workload("curriculum", dev)
     B, L, M = 512, wl["L"], wl["M"]
     p = wl["pulses"][:B].double().to(dev)
