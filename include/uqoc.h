@@ -25,6 +25,8 @@
  *     (PLE)  [SCORE.py:113-114].
  *   - Hamiltonian is the CODE's form (SCORE.py:117-124):
  *       H = 1/2 (1+eps) (cos(phi) X + sin(phi) Y + delta Z),  U_i = exp(-i H tau_i)
+ *   - domain: the table / polynomial sin/cos paths reduce the rotation angle with a magic-number round;
+ *     |tau (1+eps) sqrt(1+delta^2)| must stay below ~6000 rad per pulse (the reference's pulse ranges give < 3)
  */
 #ifndef UQOC_H_
 #define UQOC_H_

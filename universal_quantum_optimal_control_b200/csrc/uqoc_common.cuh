@@ -125,6 +125,33 @@ struct SinCos<double, SC_TABLE> {
         s = ::fma(ct, sr, st * cr);
         c = ::fma(-st, sr, ct * cr);
     }
+    // Same table, angle given as tau * (index slope ap = a 1024/pi): k = round(tau ap) from the magic-number FMA,
+    // the residual frac = fma(tau, ap, -k) with ONE rounding (the Cody-Waite triple is not needed because the angle
+    // is never formed), sin r to r^3 (truncation 7e-17 at |r| <= pi/2048).  13 DFMA-pipe instructions including
+    // the product with tau (the eval() path needs 16).
+    __device__ __forceinline__ static void eval_slope(double tau, double ap, double& s, double& c, int& kbits, const double* tab) {
+        const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+        const double kf = ::fma(tau, ap, MAGIC);
+        const int k = __double2loint(kf);
+        kbits = k >> 10;
+        const double frac = ::fma(tau, ap, MAGIC - kf);
+        const double r = frac * 0.0030679615757712823;          // pi/1024
+        const double st = tab[k & 1023], ct = tab[1024 + (k & 1023)];
+        const double z = r * r;
+        const double sr = ::fma(r * z, -1.6666666666666666e-01, r);
+        const double cr = ::fma(z, ::fma(z, 4.1666666666666664e-02, -0.5), 1.0);
+        s = ::fma(ct, sr, st * cr);
+        c = ::fma(-st, sr, ct * cr);
+    }
+    // full-sign variant (the backward sweep looks up the DOUBLE angle): sign (-1)^(k div 1024) restored by an
+    // integer XOR on the high words (ALU pipe, not FP64)
+    __device__ __forceinline__ static void eval_slope_signed(double tau, double ap, double& s, double& c, const double* tab) {
+        int kb;
+        eval_slope(tau, ap, s, c, kb, tab);
+        const int sg = kb << 31;
+        s = __hiloint2double(__double2hiint(s) ^ sg, __double2loint(s));
+        c = __hiloint2double(__double2hiint(c) ^ sg, __double2loint(c));
+    }
 };
 
 // ---------------------------------------------------------------- small math traits

@@ -134,6 +134,7 @@ template <typename T, int ST, int LPS, int SC, bool BWD>
 __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
     using R = Real<T>;
     using SCP = SinCos<T, SC>;
+    constexpr bool kSlopeTable = (sizeof(T) == 8) && (SC == SC_TABLE);   // FP64 table policy: slope-indexed look-ups
     constexpr int NB = GradBuf<LPS>::NB;
     constexpr int SPB = kThreads / LPS;  // sample slots per block
     constexpr int TS = SPB * ST;         // samples per tile
@@ -233,10 +234,14 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
             const Row4<T> row = fwd_tab[rowbase + jj];
 #pragma unroll
             for (int u = 0; u < ST; ++u) {
-                const T h = row.z * kc[u].a;
                 T s, c;
                 int kb;
-                SCP::eval(h, s, c, kb, sctab);
+                if constexpr (kSlopeTable) {
+                    SCP::eval_slope(row.z, kc[u].ap, s, c, kb, sctab);
+                } else {
+                    const T h = row.z * kc[u].a;
+                    SCP::eval(h, s, c, kb, sctab);
+                }
                 if (SCP::kTracksParity && !BWD) parity[u] ^= kb;
                 const T sp = s * kc[u].r;
                 const T q1 = sp * row.x, q2 = sp * row.y, q3 = sp * kc[u].delta;
@@ -328,13 +333,20 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
                     T gp = (T)0, gt = (T)0;
 #pragma unroll
                     for (int u = 0; u < ST; ++u) {
-                        const T h = row.z * kc[u].a;
-                        T s, c;
-                        int kb;
-                        SCP::eval(h, s, c, kb, sctab);
-                        const T s2 = s + s;
-                        const T C2 = R::fma(-s2, s, (T)1);        // cos 2h
-                        const T Sr = (s2 * kc[u].r) * c;          // sin 2h / w
+                        T C2, Sr;
+                        if constexpr (kSlopeTable) {
+                            T S2;                                     // (sin 2h, cos 2h) straight from the table
+                            SCP::eval_slope_signed(row.z, kc[u].a2p, S2, C2, sctab);
+                            Sr = S2 * kc[u].r;
+                        } else {
+                            const T h = row.z * kc[u].a;
+                            T s, c;
+                            int kb;
+                            SCP::eval(h, s, c, kb, sctab);
+                            const T s2 = s + s;
+                            C2 = R::fma(-s2, s, (T)1);                // cos 2h
+                            Sr = (s2 * kc[u].r) * c;                  // sin 2h / w
+                        }
                         const T k1 = R::fma(-C2, kc[u].r2, kc[u].r2);  // (1 - cos 2h)/w^2
                         const T dl = kc[u].delta;
                         const T t = R::fma(dl, W3[u], A[u]);      // w <W, n>
