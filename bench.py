@@ -148,6 +148,14 @@ def cpu_baseline(workload_name: str, L: int, budget_s: float = 12.0):
                       f"best of {reps} after warm-up; host has {os.cpu_count()} logical cores"}
 
 
+def workload_config(name: str, B: int, L: int, M: int, M_total: int, world: int) -> dict:
+    """The `config` object both arms print: names the workload (no model keys)."""
+    return {"workload": ("BASELINE config 5 slice (curriculum, Philox eps on-chip)" if name == "curriculum"
+                         else "BASELINE config 3 (GRAPE, explicit eps)"),
+            "targets_B": B, "pulses_L": L, "samples_per_target_per_gpu": M, "samples_per_target_total": M_total,
+            "props_per_step": float(B) * M_total * L, "loss": "sharp", "sharding": f"samples x{world}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +187,10 @@ def run_reference(args):
         "impl": "reference", "metric": "SU(2) propagations/s fwd+bwd", "value": val, "unit": "prop/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "L": L, "note": "CPU reference path (torch port of the reference op sequence)"},
+        # same workload description as the uqoc arm (workload_config); the bounded per-step sample is stated beside it
+        "config": dict(workload_config(args.workload, wl[0], L, wl[2], wl[2] * max(1, args.gpus), max(1, args.gpus)),
+                       reference_arm_sample=f"B={B} x M={M} x L={L} per step on the host CPU",
+                       note="CPU reference path (torch port of the reference op sequence, oracle/torch_port.py)"),
         "cpu_baseline": {"value": val, "unit": "prop/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "prop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -360,12 +371,10 @@ def main():
             "metric": "SU(2) propagations/s fwd+bwd", "value": value, "unit": "prop/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": ("BASELINE config 5 slice (curriculum, Philox eps on-chip)" if args.workload == "curriculum"
-                                    else "BASELINE config 3 (GRAPE, explicit eps)"),
-                       "targets_B": B, "pulses_L": L, "samples_per_target_per_gpu": M, "samples_per_target_total": M_total,
-                       "props_per_step": props_step, "loss": "sharp", "sincos": "mufu" if args.fast_sincos else ("poly" if (args.flags & 4) else "table"),
-                       "sharding": f"samples x{world}", "l2_flush_between_steps": True,
-                       "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "config": dict(workload_config(args.workload, B, L, M, M_total, world),
+                           sincos="mufu" if args.fast_sincos else ("poly" if (args.flags & 4) else "table"),
+                           l2_flush_between_steps=True,
+                           timing="CUDA events per step on the launching stream, max over ranks"),
             "e2e": {"value": props_step / (min(e2e_ms, e2e_graph_ms or e2e_ms) * 1e-3), "unit": "prop/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": min(e2e_ms, e2e_graph_ms or e2e_ms),
                     "api": "GraphedFusedStep" if (e2e_graph_ms or 1e30) < e2e_ms else "fused_propagate_loss + backward",
