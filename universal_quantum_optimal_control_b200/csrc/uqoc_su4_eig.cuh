@@ -94,6 +94,10 @@ struct Su4Frame {
     T dl[3];         // lam[m] - lam[m+1]  (the backward sweep only needs phase DIFFERENCES)
     T dl_lo[3];
     T te;            // 1 + eps
+    // isoclinic factors of V in SO(4) = (SU(2) x SU(2))/Z2:  V K V^T for antisymmetric K = sum alpha_a L_a +
+    // sum beta_b R_b rotates alpha by Rl and beta by Rr; symmetric S = t/4 I + sum N_ab L_a R_b goes to Rl N Rr^T
+    // (L_a / R_b = left / right multiplication by the quaternion units).  hRr = Rr / 2.
+    T Rl[3][3], hRr[3][3];
 };
 
 template <typename T>
@@ -117,6 +121,40 @@ __device__ __forceinline__ void su4_make_frame(Su4Frame<T>& f, T d1, T d2, T eps
         f.dl_lo[m] = (T)(l - (double)f.dl[m]);
     }
     f.te = (T)1 + eps;
+    // Rot[c][a] = 1/4 <U_c, V U_a V^T> with U = L or R; both are antisymmetric with two upper non-zeros (i, j, sign)
+    constexpr int UL[3][2][3] = {{{0, 1, -1}, {2, 3, -1}}, {{0, 2, -1}, {1, 3, 1}}, {{0, 3, -1}, {1, 2, -1}}};
+    constexpr int UR[3][2][3] = {{{0, 1, -1}, {2, 3, 1}}, {{0, 2, -1}, {1, 3, -1}}, {{0, 3, -1}, {1, 2, 1}}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double rl = 0.0, rr = 0.0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                {
+                    const int i = UL[c][e][0], j = UL[c][e][1];
+                    double m = 0.0;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int pp = UL[a][g][0], qq = UL[a][g][1];
+                        m += UL[a][g][2] * (V[i][pp] * V[j][qq] - V[i][qq] * V[j][pp]);
+                    }
+                    rl += UL[c][e][2] * m;
+                }
+                {
+                    const int i = UR[c][e][0], j = UR[c][e][1];
+                    double m = 0.0;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int pp = UR[a][g][0], qq = UR[a][g][1];
+                        m += UR[a][g][2] * (V[i][pp] * V[j][qq] - V[i][qq] * V[j][pp]);
+                    }
+                    rr += UR[c][e][2] * m;
+                }
+            }
+            f.Rl[c][a] = (T)(0.5 * rl);
+            f.hRr[c][a] = (T)(0.25 * rr);
+        }
 }
 
 // full-sign sin/cos of the eigenphases from the shared-memory table {sin[1024] | cos[1024]} of (k pi/1024).
@@ -334,6 +372,58 @@ __device__ __forceinline__ void herm_conj_real(Herm4<T>& E, const Herm4<T>& A, c
         }
 }
 
+// E = W^T A W (TR = false, W = V: into the eigenbasis) or W A W^T (TR = true: back out) through the isoclinic
+// coordinates: elements -> (alpha, beta, N) by add/sub butterflies, three 3x3 rotations (72 FMA), butterflies back.
+// ~117 FMA-pipe operations instead of the 176 of herm_conj_real.  tq = Tr(A)/4 (invariant of the whole sweep).
+template <typename T, bool TR>
+__device__ __forceinline__ void herm_conj_iso(Herm4<T>& E, const Herm4<T>& A, const Su4Frame<T>& f, T tq) {
+    // pair index: (0,1)=0 (0,2)=1 (0,3)=2 (1,2)=3 (1,3)=4 (2,3)=5;  re = S off-diagonal, im = K
+    const T k01 = A.im[0], k02 = A.im[1], k03 = A.im[2], k12 = A.im[3], k13 = A.im[4], k23 = A.im[5];
+    const T s01 = A.re[0], s02 = A.re[1], s03 = A.re[2], s12 = A.re[3], s13 = A.re[4], s23 = A.re[5];
+    const T al[3] = {(T)-0.5 * (k01 + k23), (T)0.5 * (k13 - k02), (T)-0.5 * (k03 + k12)};
+    const T b2[3] = {k23 - k01, -(k02 + k13), k12 - k03};                                  // 2 beta
+    const T u0 = A.dg[0] + A.dg[1], u1 = A.dg[0] - A.dg[1], u2 = A.dg[2] + A.dg[3], u3 = A.dg[2] - A.dg[3];
+    const T N2[3][3] = {{(T)0.5 * (u2 - u0), s03 - s12, -(s02 + s13)},
+                        {-(s03 + s12), (T)-0.5 * (u1 + u3), s01 - s23},
+                        {s02 - s13, -(s01 + s23), (T)0.5 * (u3 - u1)}};                     // 2 N
+    T ao[3], bo[3], Y[3][3], N[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T a = (T)0, b = (T)0;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            a += (TR ? f.Rl[c][e] : f.Rl[e][c]) * al[e];
+            b += (TR ? f.hRr[c][e] : f.hRr[e][c]) * b2[e];
+        }
+        ao[c] = a;
+        bo[c] = b;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            T y = (T)0;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) y += N2[a][e] * (TR ? f.hRr[b][e] : f.hRr[e][b]);
+            Y[a][b] = y;
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            T n = (T)0;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) n += (TR ? f.Rl[a][e] : f.Rl[e][a]) * Y[e][b];
+            N[a][b] = n;
+        }
+    E.im[0] = -ao[0] - bo[0]; E.im[1] = -ao[1] - bo[1]; E.im[2] = -ao[2] - bo[2];
+    E.im[3] = bo[2] - ao[2];  E.im[4] = ao[1] - bo[1];  E.im[5] = bo[0] - ao[0];
+    const T pp = N[1][1] + N[2][2], mm = N[1][1] - N[2][2], cm = tq - N[0][0], cp = tq + N[0][0];
+    E.dg[0] = cm - pp; E.dg[1] = cm + pp; E.dg[2] = cp - mm; E.dg[3] = cp + mm;
+    E.re[0] = N[1][2] - N[2][1]; E.re[1] = N[2][0] - N[0][2]; E.re[2] = N[0][1] - N[1][0];
+    E.re[3] = -N[0][1] - N[1][0]; E.re[4] = -N[0][2] - N[2][0]; E.re[5] = -N[1][2] - N[2][1];
+}
+
 // ------------------------------------------------------------------ kernel
 constexpr int kSu4eThreads = 64;
 constexpr int kSu4eWarps = kSu4eThreads / 32;
@@ -347,8 +437,9 @@ __host__ __device__ inline size_t su4e_smem_bytes(int L, bool bwd) {
     return n * sizeof(T) + 16;
 }
 
+// FP32: 6 resident blocks per SM (<= 170 registers) measured best; FP64 needs the full register file
 template <typename T, bool BWD>
-__global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p) {
+__global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? 6 : 1) su4e_kernel(const Su4Params<T> p) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int L = p.L;
     T* tab = reinterpret_cast<T*>(smem_raw);                // {sin[1024] | cos[1024]} of k pi/1024
@@ -572,13 +663,14 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
                     }
                 }
             }
+            const T tq = (T)0.25 * (A.dg[0] + A.dg[1] + A.dg[2] + A.dg[3]);       // Tr A / 4: invariant of the sweep
             for (int k = L - 1; k >= 0; --k) {
                 T wr[6], wi[6];
                 su4_phase_diffs<T>(f, tauv[k], wr, wi, tab);
                 const T z1a = A.dg[0] + A.dg[1] - A.dg[2] - A.dg[3];
                 const T z2a = A.dg[0] - A.dg[1] + A.dg[2] - A.dg[3];
                 Herm4<T> E;
-                herm_conj_real<T, false>(E, A, f);
+                herm_conj_iso<T, false>(E, A, f, tq);
                 T g_tau = f.te * (E.dg[0] * f.lam[0] + E.dg[1] * f.lam[1] + E.dg[2] * f.lam[2] + E.dg[3] * f.lam[3]);
                 // E'_mn = E_mn e^{i(h_m - h_n)}
 #pragma unroll
@@ -588,7 +680,7 @@ __global__ void __launch_bounds__(kSu4eThreads) su4e_kernel(const Su4Params<T> p
                     E.im[pq] = er * wi[pq] + ei * wr[pq];
                 }
                 Herm4<T> X;
-                herm_conj_real<T, true>(X, E, f);
+                herm_conj_iso<T, true>(X, E, f, tq);
                 const T z1b = X.dg[0] + X.dg[1] - X.dg[2] - X.dg[3];
                 const T z2b = X.dg[0] - X.dg[1] + X.dg[2] - X.dg[3];
                 T g_p1 = (T)0.5 * (z1a - z1b), g_p2 = (T)0.5 * (z2a - z2b);
