@@ -208,6 +208,9 @@ def main():
     ap.add_argument("--fast-sincos", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="tuning flags (tuning_flags())")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
+                    help="N>1: all-reduce of [Fsum|G] through NCCL, or fused into the partials reduction over NVLink peer "
+                         "memory (uqoc_su2_fwdbwd_peer); auto = peer when the vector is small (<= 2^18 reals)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -246,6 +249,12 @@ def main():
     buf = torch.empty(B + B * L * 2, dtype=rdt, device=dev)
     Fsum, G = buf[:B], buf[B:]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+    # N>1 exchange step: NCCL all-reduce, or fused into the partials reduction over NVLink peer memory
+    px = None
+    if group is not None and args.exchange != "nccl":
+        from universal_quantum_optimal_control_b200 import peer as peer_mod
+        if args.exchange == "peer" or (B + B * L * 2) <= peer_mod.MAX_N:
+            px = uq.PeerExchange(group, B, L, 2, rdt, dev)
 
     loss_dev = torch.empty(3, dtype=rdt, device=dev)
 
@@ -253,8 +262,11 @@ def main():
         if group is None:      # single GPU: fused kernel + (fused) partials reduction / loss epilogue, 2 launches
             ops._launch_fwdbwd_loss(pulses_d, tc, err_d, M, wl["sigma"], 1234, i, "sharp", 0.99, 100, None, None, Fsum, G, loss_dev, flags)
             return loss_dev
-        ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags)
-        dist.all_reduce(buf, group=group)
+        if px is not None:
+            ops._launch_fwdbwd_peer(pulses_d, tc, err_d, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags, px)
+        else:
+            ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags)
+            dist.all_reduce(buf, group=group)
         return ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
 
     def barrier():
@@ -279,10 +291,14 @@ def main():
         flush.fill_(i & 0xFF)
         ev[i][0].record()
         kev[i][0].record()
-        ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags)
-        kev[i][1].record()
-        if group is not None:
-            dist.all_reduce(buf, group=group)
+        if px is not None:
+            ops._launch_fwdbwd_peer(pulses_d, tc, err_d, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags, px)
+            kev[i][1].record()                     # fused kernel + fused reduction/exchange kernel
+        else:
+            ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags)
+            kev[i][1].record()
+            if group is not None:
+                dist.all_reduce(buf, group=group)
         loss_out = ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
         ev[i][1].record()
     if group is None:
@@ -308,12 +324,13 @@ def main():
         T = target_h.to(dev, non_blocking=True)
         if err_h is None:
             val, _ = uq.fused_propagate_loss(p, T, monte_carlo=M_total, sigma=wl["sigma"], seed=1234, offset=i,
-                                             loss="sharp", flags=flags, group=group)
+                                             loss="sharp", flags=flags, group=px if px is not None else group)
         elif world == 1:
             val, _ = uq.fused_propagate_loss(p, T, error=err_h.to(dev, non_blocking=True), monte_carlo=M_total,
                                              loss="sharp", flags=flags)
         else:   # explicit eps at N>1: every rank copies in only its own shard of the (2, B*M_total) tensor
-            val, _ = _sharded_explicit(uq, ops, p, T, err_h.to(dev, non_blocking=True), M, M_total, rank, group, flags)
+            val, _ = _sharded_explicit(uq, ops, p, T, err_h.to(dev, non_blocking=True), M, M_total, rank,
+                                       px if px is not None else group, flags)
         val.backward()
         grad_h.copy_(p.grad, non_blocking=True)
         loss_h.copy_(val.detach().reshape(1), non_blocking=True)
@@ -373,6 +390,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": dict(workload_config(args.workload, B, L, M, M_total, world),
                            sincos="mufu" if args.fast_sincos else ("poly" if (args.flags & 4) else "table"),
+                           exchange=(None if group is None else ("nvlink peer memory, fused into the partials reduction"
+                                                                 if px is not None else "nccl all-reduce")),
                            l2_flush_between_steps=True,
                            timing="CUDA events per step on the launching stream, max over ranks"),
             "e2e": {"value": props_step / (min(e2e_ms, e2e_graph_ms or e2e_ms) * 1e-3), "unit": "prop/s", "h2d_bytes_per_step": h2d,
@@ -380,13 +399,14 @@ def main():
                     "api": "GraphedFusedStep" if (e2e_graph_ms or 1e30) < e2e_ms else "fused_propagate_loss + backward",
                     "autograd_api_ms": e2e_ms, "graph_api_ms": e2e_graph_ms,
                     "timing": "host wall clock around K steps, pinned host buffers in, pinned host buffers out"},
-            "gpu_launches": args.steps * (2 if world == 1 else 2 + (1 if ops._lib.lib().uqoc_su2_workspace_bytes(B, L, M, 0, flags) > 0 else 0)),
+            "gpu_launches": args.steps * (2 if world == 1 else (3 if px is not None else
+                                          2 + (1 if ops._lib.lib().uqoc_su2_workspace_bytes(B, L, M, 0, flags) > 0 else 0))),
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s", "frac": ach_tflops / peak,
                          "traffic": ncu_dram_traffic(args.workload) if (rdt == torch.float32 and not args.flags and not args.fast_sincos) else None,
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_su2_fwdbwd_bench_launch_ncu.txt)",
                          "algorithmic_bytes_per_launch": float(B * L * 2 * 4 * 2 + B * 8 * 4 + B * 4),
                          "kernel": "su2_kernel_x2 (fused fwd+bwd, packed f32x2, table sin/cos)" if rdt == torch.float32 else "su2_kernel<double> (fused fwd+bwd)",
-                         "kernel_ms": kern_ms,
+                         "kernel_ms": kern_ms, "kernel_ms_includes_exchange": px is not None,
                          "flop_per_prop": FLOP_PER_PROP_FWDBWD,
                          "peak_source": f"nominal FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure)",
                          "measured_ffma_tflops": peak_meas, "measured_ffma2_tflops": peak2},

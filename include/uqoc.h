@@ -129,6 +129,32 @@ int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* e
                          void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Multi-GPU step with the exchange fused into the partials reduction, over NVLink / NVSwitch PEER MEMORY
+ * instead of ncclAllReduce: uqoc_su2_fwdbwd for this rank's sample shard (j0, M), then ONE kernel that reduces
+ * the sample-tile partials, pushes the (B + B*L*2) results into every rank's exchange buffer, raises per-block
+ * flags at system scope, waits for the same block of every rank and sums the slots in rank order.  On return
+ * (stream order) Fsum / G hold the sums over ALL ranks, bit-identical on every rank; follow with
+ * uqoc_loss_finalize(n_total = B * M_global).  There is no reference counterpart (the reference is single
+ * process, single device): it replaces the all-reduce this build adds for sample sharding when the
+ * exchange vector is small (latency-bound, e.g. BASELINE config 3), NCCL stays the choice for MB-sized vectors.
+ *   peer_data[q]  (HOST array, world entries): device address, valid in THIS process, of rank q's exchange
+ *                 buffer of >= uqoc_peer_data_bytes(B + B*L*2, world, dtype) bytes (CUDA VMM / IPC peer mapping,
+ *                 e.g. torch.distributed._symmetric_memory rendezvous -> buffer_ptrs)
+ *   peer_flags[q] likewise, rank q's flag buffer of uqoc_peer_flag_bytes(world) bytes, zeroed once before first use
+ *   epoch         non-zero, the same on every rank, different from the previous call's (e.g. a call counter)
+ * All ranks must make the same sequence of calls with the same (B, L, dtype); at most 16 ranks.
+ * ------------------------------------------------------------------------ */
+int64_t uqoc_peer_data_bytes(int64_t n, int world, int dtype);
+int64_t uqoc_peer_flag_bytes(int world);
+int uqoc_su2_fwdbwd_peer(const void* pulses, const void* target_c, const void* err, const void* weight,
+                         int64_t B, int64_t L, int64_t M, int64_t j0,
+                         double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                         void* F_out, void* err_out, void* Fsum, void* G,
+                         void* workspace, int64_t workspace_bytes,
+                         int rank, int world, const uint64_t* peer_data, const uint64_t* peer_flags, uint32_t epoch,
+                         int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
  * Forward only with pulses shared per target (trainer.py:113-120 evaluate;
  * util.py:214-223 / 244-249 sweeps where one sequence is expand()ed).
  *   U_out  NULL or (B*M, 2, 2, 2): composite unitary U_L...U_1 (SCORE.py:145)

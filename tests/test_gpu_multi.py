@@ -50,6 +50,24 @@ def _worker(rank, world, port, ret):
         g0 = p.grad.clone()
         dist.broadcast(g0, 0)
         out[mode] += (bool(torch.equal(g0, p.grad)),)
+    # the same step with the exchange over NVLink peer memory (uqoc_su2_fwdbwd_peer) instead of NCCL: several calls
+    # in a row (slot sets alternate with the epoch), different pulses each time, results identical on all ranks
+    px = uq.PeerExchange(dist.group.WORLD, B, L, 2, torch.float32, dev)
+    peer = []
+    for it in range(5):
+        pulses_it = pulses + 0.01 * it
+        p = pulses_it.to(dev).requires_grad_(True)
+        loss, mf = uq.fused_propagate_loss(p, T.to(dev), monte_carlo=M, sigma=(0.7, 0.05), seed=5, offset=3 + it, group=px)
+        loss.backward()
+        p1 = pulses_it.to(dev).requires_grad_(True)
+        loss1, mf1 = uq.fused_propagate_loss(p1, T.to(dev), monte_carlo=M, sigma=(0.7, 0.05), seed=5, offset=3 + it)
+        loss1.backward()
+        g0 = p.grad.clone()
+        dist.broadcast(g0, 0)
+        peer.append((abs(loss.item() - loss1.item()) / abs(loss1.item()),
+                     ((p.grad - p1.grad).abs().max() / p1.grad.abs().max()).item(),
+                     (mf - mf1).abs().max().item(), bool(torch.equal(g0, p.grad))))
+    out["peer"] = peer
     ret[rank] = out
     dist.barrier()
     dist.destroy_process_group()
@@ -65,3 +83,6 @@ def test_sharded_fused_op_matches_single_gpu():
             dl, dg, dmf, same = ret[rank][mode]
             assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6, (rank, mode, dl, dg, dmf)
             assert same, (rank, mode)
+        for dl, dg, dmf, same in ret[rank]["peer"]:
+            assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6, (rank, "peer", dl, dg, dmf)
+            assert same, (rank, "peer")

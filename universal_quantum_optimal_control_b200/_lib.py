@@ -27,6 +27,11 @@ SIGNATURES = {
     "uqoc_su2_workspace_bytes": (_i64, [_i64, _i64, _i64, _int, _uint]),
     "uqoc_su2_fwdbwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
                                _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
+    "uqoc_peer_data_bytes": (_i64, [_i64, _int, _int]),
+    "uqoc_peer_flag_bytes": (_i64, [_int]),
+    "uqoc_su2_fwdbwd_peer": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
+                                    _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                    C.c_uint32, _int, _uint, _vp]),
     "uqoc_su2_fwdbwd_loss": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64, _int, _dbl, _dbl,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_su2_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,

@@ -353,13 +353,20 @@ struct LossSpec {
     int kind;
     void* loss_out;
 };
+// peer-memory exchange of [G | Fsum] fused into the partials reduction (uqoc_su2_fwdbwd_peer)
+struct PeerSpec {
+    int rank, world;
+    const uint64_t* data;     // host arrays [world] of device addresses
+    const uint64_t* flags;
+    unsigned epoch;
+};
 
 template <typename T>
 static int su2_run(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
                    int64_t M, int64_t j0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* U_out,
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
                    unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr,
-                   const LossSpec* ls = nullptr) {
+                   const LossSpec* ls = nullptr, const PeerSpec* peer = nullptr) {
     const Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
     Su2Params<T> p;
     p.pulses = (const T*)pulses;
@@ -392,6 +399,23 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     else if (flags & UQOC_FLAG_FAST_SINCOS) rc = su2_launch<T, SC_MUFU>(p, plan, bwd, stream);
     else rc = su2_launch<T, SC_POLY>(p, plan, bwd, stream);
     if (rc != 0) return rc;
+    if (peer != nullptr) {
+        PeerParams<T> pp;
+        for (int q = 0; q < peer->world; ++q) {
+            pp.data[q] = (T*)(uintptr_t)peer->data[q];
+            pp.flags[q] = (unsigned*)(uintptr_t)peer->flags[q];
+        }
+        pp.rank = peer->rank; pp.world = peer->world; pp.epoch = peer->epoch;
+        const long long n = n_g + B;
+        pp.n_pad = (n + 31) / 32 * 32;
+        long long blocks = (n + 31) / 32;
+        const long long cap = (long long)sm_count() * 2;          // 1024-thread blocks: 2 resident per SM
+        if (blocks > cap) blocks = cap;
+        if (blocks > kPeerMaxBlocks) blocks = kPeerMaxBlocks;
+        su2_reduce_exchange<T, 32><<<(unsigned)blocks, 1024, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, pp,
+                                                                        (T*)Fsum, (T*)G);
+        return launch_status("su2_reduce_exchange");
+    }
     if (plan.splits > 1 && (Fsum != nullptr || n_g > 0)) {
         if (ls != nullptr && (int64_t)plan.splits * B <= 65536 && Fsum != nullptr) {
             const long long n = n_g + B;
@@ -471,6 +495,32 @@ int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, c
                                Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream);
     return su2_run<float>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
                           G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream);
+}
+
+int64_t uqoc_peer_data_bytes(int64_t n, int world, int dtype) {
+    if (n < 1 || world < 1) return 0;
+    return 2 * (int64_t)world * ((n + 31) / 32 * 32) * (dtype == UQOC_F64 ? 8 : 4);
+}
+int64_t uqoc_peer_flag_bytes(int world) { return world < 1 ? 0 : (int64_t)world * kPeerMaxBlocks * (int64_t)sizeof(unsigned); }
+
+int uqoc_su2_fwdbwd_peer(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
+                         int64_t M, int64_t j0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* F_out,
+                         void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int rank, int world,
+                         const uint64_t* peer_data, const uint64_t* peer_flags, uint32_t epoch, int dtype, unsigned flags,
+                         void* stream) {
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && target_c && Fsum && G, "pulses, target_c, Fsum and G must be non-null");
+    UQOC_CHECK_ARG(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world %d/%d (max %d ranks)", rank,
+                   world, kPeerMaxWorld);
+    UQOC_CHECK_ARG(peer_data && peer_flags && epoch != 0, "peer_data, peer_flags must be non-null and epoch non-zero");
+    for (int q = 0; q < world; ++q) UQOC_CHECK_ARG(peer_data[q] && peer_flags[q], "null peer pointer for rank %d", q);
+    PeerSpec ps{rank, world, peer_data, peer_flags, epoch};
+    if (dtype == UQOC_F64)
+        return su2_run<double>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out,
+                               Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, nullptr, &ps);
+    return su2_run<float>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
+                          G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, nullptr, &ps);
 }
 
 int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M,

@@ -514,6 +514,97 @@ __global__ void __launch_bounds__(1024) su2_reduce_finalize(const T* __restrict_
     }
 }
 
+// ---- fused second stage + cross-GPU exchange over NVLink peer memory -------------------------------------
+// Replaces  su2_reduce_partials -> ncclAllReduce(SUM)  of the multi-GPU step for small exchange vectors (the
+// NCCL all-reduce of a 2 KB buffer costs ~45 us of latency at 8 GPUs; BASELINE config 3 is a 50 us kernel).
+// Every rank maps every other rank's exchange buffer (CUDA VMM peer mapping; the host side gets the pointers
+// from torch.distributed._symmetric_memory).  One-shot, push model, no grid-wide or cross-block sync:
+//   block g reduces its outputs over the sample-tile partials (fixed order), STORES them into slot[rank] of
+//   every rank's buffer (coalesced 128 B rows over NVLink), fences at system scope, raises flag[rank][g] on every
+//   rank, spins on its own flag[q][g] for all q, then sums the slots in rank order 0..R-1 -- the same order on
+//   every rank, so all ranks end with bit-identical [G | Fsum].
+// Two slot sets alternate with the epoch (a rank can only be one call ahead of the slowest peer).  The grid is
+// capped at the resident capacity so every waiting block has its remote partner running.
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerMaxBlocks = 1024;      // flag row length; grid <= this
+
+template <typename T>
+struct PeerParams {
+    T* data[kPeerMaxWorld];               // rank q's exchange buffer as mapped in this process: [2][world][n_pad]
+    unsigned* flags[kPeerMaxWorld];       // rank q's flag buffer: [world][kPeerMaxBlocks]
+    int rank, world;
+    unsigned epoch;
+    long long n_pad;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int YL>
+__global__ void __launch_bounds__(32 * YL) su2_reduce_exchange(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
+                                                               int splits, int B, long long n_g, const PeerParams<T> pp,
+                                                               T* __restrict__ Fsum, T* __restrict__ G) {
+    static_assert(YL >= kPeerMaxWorld, "one warp per peer in the push / pull phases");
+    __shared__ T red[YL][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const long long n = n_g + B;
+    const long long n_groups = (n + 31) / 32;
+    const size_t set_off = (size_t)(pp.epoch & 1u) * pp.world * pp.n_pad;
+    // ---- phase 1: reduce over the sample-tile partials, push to every rank's slot[rank]
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long i = g * 32 + x;
+        T tot = (T)0;
+        if (i < n_g) {
+#pragma unroll 8
+            for (int s = y; s < splits; s += YL) tot += G_part[(size_t)s * n_g + i];
+        } else if (i < n) {
+#pragma unroll 8
+            for (int s = y; s < splits; s += YL) tot += Fsum_part[(size_t)s * B + (i - n_g)];
+        }
+        red[y][x] = tot;
+        __syncthreads();
+        if (y == 0) {
+            T t = red[0][x];
+#pragma unroll
+            for (int yy = 1; yy < YL; ++yy) t += red[yy][x];
+            red[0][x] = t;
+        }
+        __syncthreads();
+        if (y < pp.world) pp.data[y][set_off + (size_t)pp.rank * pp.n_pad + i] = red[0][x];   // i < n_pad always
+        __syncthreads();
+    }
+    if (y < pp.world) __threadfence_system();       // only the warps that stored to peers
+    __syncthreads();
+    if ((int)threadIdx.x < pp.world)
+        st_release_sys(pp.flags[threadIdx.x] + (size_t)pp.rank * kPeerMaxBlocks + blockIdx.x, pp.epoch);
+    // ---- phase 2: wait for block blockIdx.x of every rank, then sum the slots in rank order
+    if ((int)threadIdx.x < pp.world) {
+        const unsigned* f = pp.flags[pp.rank] + (size_t)threadIdx.x * kPeerMaxBlocks + blockIdx.x;
+        while ((int)(ld_acquire_sys(f) - pp.epoch) < 0) {      // epochs only grow; a peer may already be one call ahead
+        }
+    }
+    __syncthreads();
+    const T* mine = pp.data[pp.rank] + set_off;
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long i = g * 32 + x;
+        if (y < pp.world) red[y][x] = __ldcg(mine + (size_t)y * pp.n_pad + i);
+        __syncthreads();
+        if (y == 0) {
+            T t = red[0][x];
+            for (int q = 1; q < pp.world; ++q) t += red[q][x];
+            if (i < n_g) G[i] = t;
+            else if (i < n) Fsum[i - n_g] = t;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 inline void launch_reduce_partials(const T* Fsum_part, const T* G_part, int splits, int B, long long n_g, T* Fsum, T* G,
                                    cudaStream_t stream) {

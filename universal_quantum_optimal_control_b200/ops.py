@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import F32, F64, FLAG_FAST_SINCOS, LOSS_KINDS, check
+from .peer import PeerExchange
 from .sharding import shard_errors, shard_range
 
 __all__ = [
@@ -166,6 +167,22 @@ def _launch_fwdbwd(pulses, tc, error, weight, M, j0, sigma, seed, offset, F_out,
                               ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su2_fwdbwd")
 
 
+def _launch_fwdbwd_peer(pulses, tc, error, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, px):
+    """This rank's shard + fused [partials reduction | NVLink peer exchange]: Fsum / G come back summed over ranks."""
+    B, L, P = pulses.shape
+    if not px.matches(B, L, P, pulses.dtype):
+        raise ValueError(f"PeerExchange was built for (B, L, P, dtype) = {(px.B, px.L, px.P, px.dtype)}, "
+                         f"got {(B, L, P, pulses.dtype)}")
+    lib = _lib.lib()
+    dt = _dt(pulses)
+    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
+    ws = _workspace(ws_bytes, pulses.device)
+    check(lib.uqoc_su2_fwdbwd_peer(_ptr(pulses), _ptr(tc), _ptr(error), None, B, L, M, j0, float(sigma[0]), float(sigma[1]),
+                                   seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes,
+                                   px.rank, px.world, px.data_ptrs, px.flag_ptrs, px.next_epoch(), dt, flags,
+                                   _stream(pulses.device)), "uqoc_su2_fwdbwd_peer")
+
+
 def _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags):
     """Single-GPU step: fused kernel + (fused) partials reduction + loss epilogue, <= 2 launches."""
     B, L, _ = pulses.shape
@@ -207,7 +224,13 @@ class _FusedPropagateLoss(torch.autograd.Function):
         if need_grad and group is None:
             loss_out = torch.empty(3, dtype=pulses.dtype, device=pulses.device)
             _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags)
+        elif need_grad and isinstance(group, PeerExchange):
+            # exchange fused into the partials reduction over NVLink peer memory (no NCCL call): peer.py
+            _launch_fwdbwd_peer(pulses, tc, error, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, group)
+            loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
         else:
+            if isinstance(group, PeerExchange):
+                group = group.group
             if need_grad:
                 _launch_fwdbwd(pulses, tc, error, None, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags)
             else:
@@ -239,7 +262,9 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     error (2, B*monte_carlo) explicit [delta; eps] with sample s = b*M + j, or None for
     on-chip Philox N(0, sigma) samples keyed by (seed, offset).  With ``group`` (a
     torch.distributed process group) every rank handles samples
-    j in [rank*M/R, (rank+1)*M/R) of every target and one all-reduce combines [Fsum | G].
+    j in [rank*M/R, (rank+1)*M/R) of every target and one all-reduce combines [Fsum | G]; with
+    ``group`` a :class:`PeerExchange` that exchange is fused into the partials reduction over NVLink
+    peer memory (small exchange vectors: few targets).
     Returns ``(loss scalar, mean fidelity per target (B,))``.
     """
     if pulses.ndim != 3 or pulses.shape[-1] != 2:
@@ -255,7 +280,9 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     p = pulses.to(rdt).contiguous()
     tc = target_coeffs(U_target, rdt)
     rank, world = 0, 1
-    if group is not None:
+    if isinstance(group, PeerExchange):                   # NVLink peer-memory exchange instead of NCCL (peer.py)
+        rank, world = group.rank, group.world
+    elif group is not None:
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     j0, M = shard_range(M_total, rank, world)
