@@ -142,7 +142,8 @@ int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* e
  *                 e.g. torch.distributed._symmetric_memory rendezvous -> buffer_ptrs)
  *   peer_flags[q] likewise, rank q's flag buffer of uqoc_peer_flag_bytes(world) bytes, zeroed once before first use
  *   epoch         non-zero, the same on every rank, different from the previous call's (e.g. a call counter)
- * All ranks must make the same sequence of calls with the same (B, L, dtype); at most 16 ranks.
+ * All ranks must make the same sequence of calls with the same (B, L, dtype); at most 16 ranks.  A rank whose
+ * peers never make the matching call gives up after 10 s and returns NaN in Fsum / G (no hung GPU).
  * ------------------------------------------------------------------------ */
 int64_t uqoc_peer_data_bytes(int64_t n, int world, int dtype);
 int64_t uqoc_peer_flag_bytes(int world);

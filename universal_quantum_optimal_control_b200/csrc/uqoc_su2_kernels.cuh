@@ -584,12 +584,23 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange(const T* __restri
     if ((int)threadIdx.x < pp.world)
         st_release_sys(pp.flags[threadIdx.x] + (size_t)pp.rank * kPeerMaxBlocks + blockIdx.x, pp.epoch);
     // ---- phase 2: wait for block blockIdx.x of every rank, then sum the slots in rank order
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
     if ((int)threadIdx.x < pp.world) {
         const unsigned* f = pp.flags[pp.rank] + (size_t)threadIdx.x * kPeerMaxBlocks + blockIdx.x;
+        unsigned long long t0 = 0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while ((int)(ld_acquire_sys(f) - pp.epoch) < 0) {      // epochs only grow; a peer may already be one call ahead
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) {                    // 10 s: a peer never made the matching call
+                s_timeout = 1;                                 // -> NaN outputs instead of a hung GPU
+                break;
+            }
         }
     }
     __syncthreads();
+    const bool timed_out = s_timeout != 0;
     const T* mine = pp.data[pp.rank] + set_off;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long i = g * 32 + x;
@@ -598,6 +609,7 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange(const T* __restri
         if (y == 0) {
             T t = red[0][x];
             for (int q = 1; q < pp.world; ++q) t += red[q][x];
+            if (timed_out) t = (T)NAN;
             if (i < n_g) G[i] = t;
             else if (i < n) Fsum[i - n_g] = t;
         }
