@@ -153,3 +153,100 @@ class FusedTrainer(FusedStepMixin):
             if self.best_state is not None:                            # trainer.py:224-225
                 self.model.load_state_dict(self.best_state)
         return history
+
+
+class GraphedTrainStep:
+    """The whole optimisation step of ``trainer.py:67-92`` as ONE CUDA-graph replay:
+    ``model(U_emb)`` -> fused propagate/loss -> ``backward()`` -> ``clip_grad_norm_`` -> ``optimizer.step()``.
+
+    At the reference's step sizes the fused op is a 60-200 us kernel while eager PyTorch spends milliseconds of
+    host time launching the pulse generator's small kernels; a captured step costs one graph launch.  The Philox
+    (seed, offset) pair lives in device memory and is advanced INSIDE the graph, so every replay draws fresh error
+    samples (``UQOC_FLAG_RNG_FROM_DEVICE``); dropout keeps working through torch's graph-safe generator.  One graph
+    is captured per (delta_std, epsilon_std) curriculum stage on first use.
+
+        step = GraphedTrainStep(model, B=200, emb_shape=(4,), monte_carlo=1000, lr=3e-5)
+        loss = step(U_emb_batch, U_target_batch, SigmaSpec(0.4, 0.05))     # device scalar; .item() when needed
+    """
+
+    def __init__(self, model, *, B: int, emb_shape: Sequence[int], monte_carlo: int = 1000, device="cuda", lr: float = 3e-5,
+                 optimizer=None, loss: str = "sharp", seed: int = 0, clip_norm: float = 1.0, emb_dtype=torch.float32,
+                 compute_dtype: Optional[torch.dtype] = None, target_dim: int = 2, flags: int = 0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs a CUDA device: the uqoc ops have no CPU fallback")
+        self.model = model.to(self.device)
+        # Adam with device-side step counters: required for optimizer.step() inside a CUDA graph (trainer.py:46 lr)
+        self.optimizer = optimizer or torch.optim.Adam(self.model.parameters(), lr=lr, capturable=True)
+        self.M, self.loss, self.clip_norm, self.dtype, self.flags = int(monte_carlo), loss, clip_norm, compute_dtype, flags
+        cdt = torch.complex128 if compute_dtype == torch.float64 else torch.complex64
+        self.s_emb = torch.zeros(B, *emb_shape, dtype=emb_dtype, device=self.device)
+        self.s_target = torch.zeros(B, target_dim, target_dim, dtype=cdt, device=self.device)
+        self.s_target[:] = torch.eye(target_dim, dtype=cdt, device=self.device)
+        self.d_rng = torch.tensor([seed, 0], dtype=torch.int64, device=self.device)
+        self.s_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.s_fid = torch.zeros(B, dtype=torch.float32, device=self.device)
+        self._graphs = {}
+        self._stream = torch.cuda.Stream(self.device)
+
+    def _step_body(self, sigma):
+        self.d_rng[1] += 1                                            # fresh Philox offset on every replay
+        pulses = self.model(self.s_emb)
+        fn = ops.fused_propagate_loss_su4 if pulses.shape[-1] == 3 else ops.fused_propagate_loss
+        kw = dict(monte_carlo=self.M, sigma=sigma, seed=self.d_rng.data_ptr(), loss=self.loss, dtype=self.dtype,
+                  flags=self.flags | 8)                               # 8 = UQOC_FLAG_RNG_FROM_DEVICE
+        if pulses.shape[-1] == 3:
+            raise NotImplementedError("device-resident Philox state is wired for the SU(2) kernels only")
+        loss, fid = fn(pulses, self.s_target, **kw)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
+        self.optimizer.step()
+        self.s_loss.copy_(loss.detach().float())
+        self.s_fid.copy_(fid.detach().float())
+
+    def _capture(self, sigma):
+        self.model.train()
+        with torch.cuda.stream(self._stream):
+            rng0 = self.d_rng.clone()
+            state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+            opt_before = {id(t): t.detach().clone() for st in self.optimizer.state.values() for t in st.values()
+                          if torch.is_tensor(t)}
+            for _ in range(3):                                        # warm-up outside capture (lazy init, pools,
+                self.optimizer.zero_grad(set_to_none=True)            # optimizer state tensors must exist before capture)
+                self._step_body(sigma)
+            self._stream.synchronize()
+            # warm-up steps must not count: restore parameters, the optimizer's moments / step counters IN PLACE
+            # (tensors created by the warm-up are zeroed = a fresh optimizer) and the Philox offset
+            self.model.load_state_dict(state)
+            for st in self.optimizer.state.values():
+                for t in st.values():
+                    if torch.is_tensor(t):
+                        if id(t) in opt_before:
+                            t.copy_(opt_before[id(t)])
+                        else:
+                            t.zero_()
+            self.d_rng.copy_(rng0)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph, stream=self._stream):
+                self._step_body(sigma)
+            # the capture itself does not execute: nothing to undo
+        self._stream.synchronize()
+        return graph
+
+    def __call__(self, U_emb: torch.Tensor, U_target: torch.Tensor, spec) -> torch.Tensor:
+        sigma = tuple(float(x) for x in (spec.sigma if isinstance(spec, SigmaSpec) else spec))
+        graph = self._graphs.get(sigma)
+        if graph is None:
+            graph = self._graphs[sigma] = self._capture(sigma)
+        self.s_emb.copy_(U_emb, non_blocking=True)
+        self.s_target.copy_(U_target, non_blocking=True)
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))
+        graph.replay()
+        torch.cuda.current_stream(self.device).wait_stream(self._stream)
+        return self.s_loss
+
+    @property
+    def mean_fidelity(self) -> torch.Tensor:
+        """Per-target mean fidelity of the last replayed step (device tensor)."""
+        return self.s_fid
