@@ -68,6 +68,36 @@ def _worker(rank, world, port, ret):
                      ((p.grad - p1.grad).abs().max() / p1.grad.abs().max()).item(),
                      (mf - mf1).abs().max().item(), bool(torch.equal(g0, p.grad))))
     out["peer"] = peer
+    # the trainer mixin picks the peer exchange by itself for small vectors; replicas stay bit-identical and track
+    # the single-process run
+    from universal_quantum_optimal_control_b200.trainer import FusedTrainer, SigmaSpec
+
+    class Tiny(torch.nn.Module):
+        num_qubits = 1
+
+        def __init__(self):
+            super().__init__()
+            self.net = torch.nn.Linear(4, 2 * L)
+
+        def forward(self, x):
+            y = torch.sigmoid(self.net(x)).view(-1, L, 2)
+            return torch.stack([(y[..., 0] * 2 - 1) * 3.15, 0.1 + 0.4 * y[..., 1]], -1)
+
+    torch.manual_seed(1)
+    m_multi, m_single = Tiny(), Tiny()
+    m_single.load_state_dict(m_multi.state_dict())
+    emb = torch.randn(B, 4, generator=g)
+    t_multi = FusedTrainer(m_multi, monte_carlo=M, device=dev, optimizer=torch.optim.Adam(m_multi.parameters(), lr=1e-2),
+                           seed=9, process_group=dist.group.WORLD)
+    t_single = FusedTrainer(m_single, monte_carlo=M, device=dev, optimizer=torch.optim.Adam(m_single.parameters(), lr=1e-2), seed=9)
+    for _ in range(3):
+        t_multi.train_epoch(emb, T, SigmaSpec(0.7, 0.05))
+        t_single.train_epoch(emb, T, SigmaSpec(0.7, 0.05))
+    w = m_multi.net.weight.detach().clone()
+    w0 = w.clone()
+    dist.broadcast(w0, 0)
+    used_peer = any(isinstance(v, uq.PeerExchange) for v in t_multi.__dict__.get("_peer_cache", {}).values())
+    out["trainer"] = ((w - m_single.net.weight.detach()).abs().max().item(), bool(torch.equal(w, w0)), used_peer)
     ret[rank] = out
     dist.barrier()
     dist.destroy_process_group()
@@ -83,6 +113,8 @@ def test_sharded_fused_op_matches_single_gpu():
             dl, dg, dmf, same = ret[rank][mode]
             assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6, (rank, mode, dl, dg, dmf)
             assert same, (rank, mode)
+        dw, same_w, used_peer = ret[rank]["trainer"]
+        assert dw < 1e-4 and same_w and used_peer, (rank, "trainer", dw, same_w, used_peer)
         for dl, dg, dmf, same in ret[rank]["peer"]:
             assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6, (rank, "peer", dl, dg, dmf)
             assert same, (rank, "peer")

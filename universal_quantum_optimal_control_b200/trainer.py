@@ -67,12 +67,36 @@ class FusedStepMixin:
         if not isinstance(spec, SigmaSpec):               # a reference-style sampler closure: explicit errors
             error = spec(self.monte_carlo * U_target.shape[0]).to(pulses.device)
         self._fused_step += 1
+        group = self._exchange_for(pulses)
         kw = {}
-        if self.fused_autotune and pulses.shape[-1] == 2 and self.fused_group is None:
+        if self.fused_autotune and pulses.shape[-1] == 2 and group is None:
             kw["flags"] = ops.autotune_flags(pulses.shape[0], pulses.shape[1], self.monte_carlo,
                                              self.fused_dtype or torch.float32, pulses.device)
         return fn(pulses, U_target, error=error, monte_carlo=self.monte_carlo, sigma=sigma, seed=self.fused_seed,
-                  offset=self._fused_step, loss=loss, dtype=self.fused_dtype, group=self.fused_group, **kw)
+                  offset=self._fused_step, loss=loss, dtype=self.fused_dtype, group=group, **kw)
+
+    fused_peer_exchange: bool = True             # multi-GPU: small exchange vectors go over NVLink peer memory
+
+    def _exchange_for(self, pulses):
+        """The process group itself (NCCL all-reduce), or - for the SU(2) path with a small [Fsum | G] vector - a
+        cached :class:`PeerExchange` over it (exchange fused into the partials reduction, peer.py)."""
+        group = self.fused_group
+        if group is None or not self.fused_peer_exchange or pulses.shape[-1] != 2 or isinstance(group, ops.PeerExchange):
+            return group
+        B, L, P = pulses.shape
+        from . import peer as _peer
+        if B + B * L * P > _peer.MAX_N:
+            return group
+        key = (B, L, P, self.fused_dtype or torch.float32)
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        if key not in cache:
+            try:
+                cache[key] = ops.PeerExchange(group, B, L, P, key[3], pulses.device)
+            except Exception as e:          # no peer mapping on this box (still a GPU path: NCCL)
+                import warnings
+                warnings.warn(f"PeerExchange unavailable ({e!r}); using the NCCL all-reduce")
+                cache[key] = group
+        return cache[key]
 
     def train_epoch(self, U_emb_batch, U_target_batch, error_distribution) -> float:   # trainer.py:58-94
         self.model.train()
