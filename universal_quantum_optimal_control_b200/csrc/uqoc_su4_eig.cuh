@@ -438,8 +438,11 @@ __host__ __device__ inline size_t su4e_smem_bytes(int L, bool bwd) {
 }
 
 // FP32: 6 resident blocks per SM (<= 170 registers) measured best; FP64 needs the full register file
+#ifndef UQOC_SU4E_MINB
+#define UQOC_SU4E_MINB 6
+#endif
 template <typename T, bool BWD>
-__global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? 6 : 1) su4e_kernel(const Su4Params<T> p) {
+__global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? UQOC_SU4E_MINB : 1) su4e_kernel(const Su4Params<T> p) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int L = p.L;
     T* tab = reinterpret_cast<T*>(smem_raw);                // {sin[1024] | cos[1024]} of k pi/1024
