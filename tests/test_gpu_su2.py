@@ -426,6 +426,31 @@ def test_tiny_and_odd_shapes(B, L, M):
     assert np.abs(grad - want_g).max() < 1e-11 * max(1.0, np.abs(want_g).max())
 
 
+# (B, L, M) chosen to land in every branch of make_plan() on a 148-SM part: lane-split scalar kernels (tiny N),
+# ST = 1 / 2 scalar-vs-packed, WPS = 4 with 2 and with 4 samples per thread (few targets x few tiles), packed ST = 4
+# with and without sample-tile splits, ragged L (chunk padding) and ragged M (partial tiles)
+PLAN_SWEEP = [(1, 48, 40), (2, 19, 600), (3, 33, 5000), (1, 96, 30000), (1, 40, 70000), (5, 36, 9000),
+              (40, 44, 1000), (100, 33, 1000), (2, 64, 40000), (300, 24, 300), (700, 17, 130), (1, 31, 80000)]
+
+
+@pytest.mark.parametrize("B,L,M", PLAN_SWEEP)
+def test_default_plan_every_regime_matches_oracle(B, L, M):
+    """Library heuristics (flags = 0), FP32 default kernels and the FP64 kernels against the oracle."""
+    rng = np.random.default_rng(B * 7919 + L * 31 + M)
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1).astype(np.float32)
+    T = rng.normal(size=(B, 2, 2)) + 1j * rng.normal(size=(B, 2, 2))
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)]).astype(np.float32)
+    want_l, want_g, want_F = orc.loss_and_grad(pulses.astype(np.float64), T, err.astype(np.float64), M, "nll")
+    val, grad, F, mf = _fused(pulses, T, err, M, torch.float32, loss="nll")
+    assert np.abs(F - want_F).max() < 3e-5                       # general complex T: |tr|^2 up to ~20, not 4
+    assert _relerr(grad, want_g) < F32_TOL_G
+    assert abs(val - want_l) < 1e-4 * max(1.0, abs(want_l))
+    assert np.abs(mf - want_F.reshape(B, M).mean(1)).max() < 1e-5
+    val64, grad64, F64, _ = _fused(pulses, T, err, M, torch.float64, loss="nll")
+    assert np.abs(F64 - want_F).max() < 1e-11 and _relerr(grad64, want_g) < 1e-10
+    assert abs(val64 - want_l) < 1e-11 * max(1.0, abs(want_l))
+
+
 def test_empty_inputs_are_rejected():
     with pytest.raises(Exception):
         uq.fused_propagate_loss(torch.zeros(0, 4, 2, device=DEV), torch.zeros(0, 2, 2, dtype=torch.complex64, device=DEV), monte_carlo=4)
