@@ -51,6 +51,9 @@ extern "C" {
 #define UQOC_FLAG_NO_TABLE 4u    /* packed kernel: polynomial sin/cos instead of the shared-memory table */
 #define UQOC_FLAG_WPS4 16u       /* packed kernel: force the pulse train to be split over the block's 4 warps */
 #define UQOC_FLAG_WPS1 32u       /* packed kernel: force one warp per sample group */
+#define UQOC_FLAG_RAW_TARGET 128u /* SU(2) shared-pulse entry points: `target_c` is the RAW complex target array
+                                    (B, 2, 2) interleaved (re, im) instead of uqoc_su2_target_coeffs' output: the
+                                    8 trace coefficients are formed in the kernel prologue (one launch less) */
 #define UQOC_FLAG_SU4_PADE 64u   /* SU(4): per-pulse scaling-and-squaring exponential kernel instead of the default
                                     eigenframe kernel (one real-symmetric eigendecomposition per error sample) */
 /* tuning overrides (0 = let the library choose): samples per thread (1,2,4) and lanes per

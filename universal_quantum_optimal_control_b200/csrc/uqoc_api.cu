@@ -381,6 +381,7 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     p.rng_dev = (flags & UQOC_FLAG_RNG_FROM_DEVICE) ? (const unsigned long long*)(uintptr_t)seed : nullptr;
     p.U_out = (T*)U_out; p.F_out = (T*)F_out; p.err_out = (T*)err_out;
     p.grid_ne = grid_ne; p.sig_tab = (const T*)sig_tab;
+    p.raw_target = (flags & UQOC_FLAG_RAW_TARGET) ? 1 : 0;
     const int64_t n_g = bwd ? B * L * 2 : 0;
     if (plan.splits > 1) {
         const int64_t need = (int64_t)plan.splits * (B + n_g) * (int64_t)sizeof(T);

@@ -44,7 +44,27 @@ struct Su2Params {
     const unsigned long long* rng_dev;   // non-null: {seed, offset} read from device memory (CUDA-graph replay)
     int grid_ne;          // > 0: err = [delta axis (M / grid_ne) | eps axis (grid_ne)], sample j -> (j / ne, j % ne)
     const T* sig_tab;     // non-null: per-target (sigma_delta, sigma_eps) rows for the Philox samples
+    int raw_target;       // != 0: target_c holds the raw complex targets (B, 2, 2, 2) (UQOC_FLAG_RAW_TARGET)
 };
+
+// trace coefficients of target b: Tr(U^dagger T) = (cr + i ci) . q.  Either precomputed rows (uqoc_su2_target_coeffs)
+// or formed here from the raw 2x2 complex target: c0 = T00+T11, c1 = i(T01+T10), c2 = T10-T01, c3 = i(T00-T11).
+template <typename T>
+__device__ __forceinline__ void su2_load_target(const Su2Params<T>& p, int b, T (&cr)[4], T (&ci)[4]) {
+    const T* t = p.target_c + (size_t)b * 8;
+    if (p.raw_target) {            // T00 (0,1) T01 (2,3) T10 (4,5) T11 (6,7)
+        cr[0] = t[0] + t[6];    ci[0] = t[1] + t[7];
+        cr[1] = -(t[3] + t[5]); ci[1] = t[2] + t[4];
+        cr[2] = t[4] - t[2];    ci[2] = t[5] - t[3];
+        cr[3] = -(t[1] - t[7]); ci[3] = t[0] - t[6];
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            cr[m] = t[m];
+            ci[m] = t[4 + m];
+        }
+    }
+}
 
 // (delta, eps) of sample (b, j): explicit tensor, 1-D axes of a meshgrid('ij') sweep, or on-chip Philox
 template <typename T>
@@ -191,11 +211,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
 
     // target coefficients: Tr(U^dagger T) = (cr + i ci) . P
     T cr[4], ci[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        cr[m] = p.target_c[(size_t)b * 8 + m];
-        ci[m] = p.target_c[(size_t)b * 8 + 4 + m];
-    }
+    su2_load_target<T>(p, b, cr, ci);
 
     const int rowbase = k * (C + 1);
     const size_t Bm = (size_t)p.B * p.M;

@@ -323,11 +323,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     __syncthreads();
 
     float cr[4], ci[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        cr[m] = p.target_c[(size_t)b * 8 + m];
-        ci[m] = p.target_c[(size_t)b * 8 + 4 + m];
-    }
+    su2_load_target<float>(p, b, cr, ci);
     const size_t Bm = (size_t)p.B * p.M;
     float fsum = 0.0f;
 

@@ -56,10 +56,10 @@ class GraphedFusedStep:
         if self.d_err is not None:
             self.d_err.copy_(self.h_err, non_blocking=True)
         self.d_rng.copy_(self.h_rng, non_blocking=True)
-        tc = ops.target_coeffs(self.d_target, self.d_pulses.dtype)
+        tc = ops.raw_target(self.d_target, self.d_pulses.dtype)        # a view: the kernel forms the trace coefficients
         Fsum, G = self.d_out[3:3 + B], self.d_out[3 + B:]
         ops._launch_fwdbwd_loss(self.d_pulses, tc, self.d_err, M, self.sigma, self.d_rng.data_ptr(), 0, self.loss, self.tau, self.k,
-                                None, None, Fsum, G, self.d_out[:3], self.flags | FLAG_RNG_FROM_DEVICE)
+                                None, None, Fsum, G, self.d_out[:3], self.flags | FLAG_RNG_FROM_DEVICE | ops.FLAG_RAW_TARGET)
         self.h_out.copy_(self.d_out, non_blocking=True)
 
     def capture(self):

@@ -125,6 +125,20 @@ def autotune_flags(B: int, L: int, M: int, dtype: torch.dtype = torch.float32, d
     return best
 
 
+FLAG_RAW_TARGET = 128
+
+
+def raw_target(U_target: torch.Tensor, real_dtype: torch.dtype) -> torch.Tensor:
+    """(B,2,2) complex targets as the interleaved real array the kernels read under ``UQOC_FLAG_RAW_TARGET``
+    (no launch when the tensor already has the matching complex dtype and is contiguous)."""
+    _require_cuda(U_target, "U_target")
+    if U_target.ndim != 3 or U_target.shape[-2:] != (2, 2):
+        raise ValueError("'U_target' must have shape (B, 2, 2)")
+    cdt = torch.complex64 if real_dtype == torch.float32 else torch.complex128
+    t = U_target if U_target.dtype == cdt else U_target.to(cdt)
+    return torch.view_as_real(t.resolve_conj().contiguous())
+
+
 def target_coeffs(U_target: torch.Tensor, real_dtype: torch.dtype) -> torch.Tensor:
     """(B,2,2) complex targets -> (B,8) trace coefficients (``uqoc_su2_target_coeffs``)."""
     _require_cuda(U_target, "U_target")
@@ -278,7 +292,8 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     if U_target.shape[0] != B:
         raise ValueError(f"U_target batch {U_target.shape[0]} != pulses batch {B}")
     p = pulses.to(rdt).contiguous()
-    tc = target_coeffs(U_target, rdt)
+    tc = raw_target(U_target, rdt)                        # (B, 2, 2, 2): the kernels form the trace coefficients themselves
+    flags = flags | FLAG_RAW_TARGET
     rank, world = 0, 1
     if isinstance(group, PeerExchange):                   # NVLink peer-memory exchange instead of NCCL (peer.py)
         rank, world = group.rank, group.world
