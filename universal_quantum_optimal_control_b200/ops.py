@@ -197,12 +197,24 @@ def _launch_fwdbwd_peer(pulses, tc, error, M, j0, sigma, seed, offset, F_out, er
                                    _stream(pulses.device)), "uqoc_su2_fwdbwd_peer")
 
 
+_WS_BYTES: dict = {}
+
+
+def _su2_ws_bytes(lib, B, L, M, dt, flags) -> int:
+    """uqoc_su2_workspace_bytes, memoised per device (the plan depends on the SM count only)."""
+    key = (B, L, M, dt, flags, torch.cuda.current_device())
+    n = _WS_BYTES.get(key)
+    if n is None:
+        n = _WS_BYTES[key] = int(lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags))
+    return n
+
+
 def _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags):
     """Single-GPU step: fused kernel + (fused) partials reduction + loss epilogue, <= 2 launches."""
     B, L, _ = pulses.shape
     lib = _lib.lib()
     dt = _dt(pulses)
-    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
+    ws_bytes = _su2_ws_bytes(lib, B, L, M, dt, flags)
     ws = _workspace(ws_bytes, pulses.device)
     check(lib.uqoc_su2_fwdbwd_loss(_ptr(pulses), _ptr(tc), _ptr(error), B, L, M, float(sigma[0]), float(sigma[1]), seed, offset,
                                    LOSS_KINDS[loss], float(tau), float(k), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G),
