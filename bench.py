@@ -156,6 +156,26 @@ def workload_config(name: str, B: int, L: int, M: int, M_total: int, world: int)
             "props_per_step": float(B) * M_total * L, "loss": "sharp", "sharding": f"samples x{world}"}
 
 
+def cpu_port_c(L: int):
+    """Informative second CPU figure: the plain-C closed-form port (oracle/uqoc_oracle.c, OpenMP, FP64) of the same
+    fwd+bwd step on all host cores.  The reference's own op sequence (cpu_baseline / --impl reference) stays THE baseline."""
+    import numpy as np
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(0)
+    B, M = 1, 16384
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (B, L)), rng.uniform(0.1, 0.5, (B, L))], -1)
+    T = np.eye(2, dtype=np.complex128)[None]
+    err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)])
+    co.fidelity_sum_and_grad(pulses, T, err, M)
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        co.fidelity_sum_and_grad(pulses, T, err, M)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": B * M * L / best, "unit": "prop/s", "cores": co.threads(), "kind": "port",
+            "sample": f"B={B} x M={M} x L={L}, FP64 complex 2x2 closed form, OpenMP, best of 3"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -419,6 +439,10 @@ def main():
                 line["other_configs"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, L)
+            try:
+                line["cpu_port_c"] = cpu_port_c(L)
+            except Exception as e:  # informative only (needs gcc or the prebuilt oracle/_build/liboracle_c.so)
+                line["cpu_port_c"] = {"error": repr(e)[:200]}
         print(json.dumps(line))
     if group is not None:
         dist.barrier()
