@@ -84,3 +84,23 @@ def test_product_never_imports_oracle():
 def test_tuning_flags_packing():
     f = uq.tuning_flags(st=4, lps=1, splits=7, fast_sincos=True)
     assert f & 1 and (f >> 8) & 0xF == 4 and (f >> 12) & 0x3F == 1 and (f >> 18) & 0xFFF == 7
+
+
+def test_python_flag_words_match_the_header():
+    """tuning_flags() / the module constants encode exactly the UQOC_FLAG_* bits of include/uqoc.h."""
+    from universal_quantum_optimal_control_b200 import graphs, ops
+    src = open(os.path.join(ROOT, "include", "uqoc.h")).read()
+    bits = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+UQOC_FLAG_([A-Z0-9_]+)\s+(\d+)u", src)}
+    assert bits["FAST_SINCOS"] == _lib.FLAG_FAST_SINCOS == uq.tuning_flags(fast_sincos=True)
+    assert bits["NO_PACKED"] == uq.tuning_flags(no_packed=True)
+    assert bits["NO_TABLE"] == uq.tuning_flags(no_table=True)
+    assert bits["RNG_FROM_DEVICE"] == graphs.FLAG_RNG_FROM_DEVICE
+    assert bits["WPS4"] == uq.tuning_flags(wps=4) and bits["WPS1"] == uq.tuning_flags(wps=1)
+    assert bits["SU4_PADE"] == uq.tuning_flags(su4_pade=True)
+    assert bits["RAW_TARGET"] == ops.FLAG_RAW_TARGET
+    assert uq.tuning_flags(st=4, lps=8, splits=37) == (4 << 8) | (8 << 12) | (37 << 18)
+    # peer-exchange sizing helpers are pure host functions
+    lib = _lib.lib()
+    assert lib.uqoc_peer_data_bytes(513, 8, _lib.F32) == 2 * 8 * 544 * 4
+    assert lib.uqoc_peer_flag_bytes(8) == 8 * 1024 * 4
+    assert lib.uqoc_peer_data_bytes(0, 8, _lib.F32) == 0
