@@ -1,11 +1,15 @@
 // Packed-FP32 (f32x2 -> SASS FFMA2/FMUL2/FADD2, new on sm_100) variant of the fused SU(2) kernel.
 //
-// Two error samples ride in the two halves of every 64-bit register pair, so one instruction
-// advances two propagations.  The FP32 FMA pipe does the same FLOPs either way, but the packed
-// form needs half the issue slots and half the register-file reads per FLOP -- the scalar kernel
-// is issue/dispatch limited (ncu: 81 % issue-active, dispatch stalls from operand-bank conflicts),
-// this one is limited by the FMA pipe itself.  Same algorithm as su2_kernel (uqoc_su2_kernels.cuh),
-// LPS = 1 only (one thread owns its samples' whole pulse train).
+// Two error samples ride in the two halves of every 64-bit register pair for the per-pulse scalars
+// (table sin/cos, q) and for the whole backward sweep, so one instruction advances two propagations;
+// the forward running product keeps two COMPONENTS of one sample per pair instead (per-sample scalar
+// in the 32-bit broadcast slot, swap / sign operand modifiers).  The FP32 FMA pipe does the same FLOPs
+// either way, but the packed form needs half the issue slots -- the scalar kernel is issue/dispatch
+// limited (ncu: 81 % issue-active), this one is limited by the FMA pipe and its operand delivery
+// (74 % pipe-active).  Same algorithm as su2_kernel (uqoc_su2_kernels.cuh), one thread
+// owns its samples' whole pulse train (WPS = 1) or a quarter of it (WPS = 4).
+// sin/cos: shared-memory table indexed by the per-sample slope (sincos2_tab), half angle in the forward
+// sweep, full angle (full-period table) in the backward sweep.
 #pragma once
 #include "uqoc_su2_kernels.cuh"
 
