@@ -266,8 +266,8 @@ def main():
     if wl["explicit"]:
         # this rank's shard of the (2, B*M_total) error tensor, generated once on the device
         err_d = uq.philox_errors(B, M, wl["sigma"], seed=1234, offset=0, j0=rank * M, device=dev, dtype=rdt)
-    buf = torch.empty(B + B * L * 2, dtype=rdt, device=dev)
-    Fsum, G = buf[:B], buf[B:]
+    buf = torch.empty(B * L * 2 + B, dtype=rdt, device=dev)      # [G | Fsum]: one exchange, G 16-byte aligned
+    G, Fsum = buf[:B * L * 2], buf[B * L * 2:]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
     # N>1 exchange step: NCCL all-reduce, or fused into the partials reduction over NVLink peer memory
     px = None
@@ -489,9 +489,10 @@ def other_configs(uq, ops, dev):
         p = wl["pulses"].to(dev)
         tc = uq.target_coeffs(wl["U_target"].to(dev), torch.float32)
         err = uq.philox_errors(B, M, wl["sigma"], 1, 0, device=dev)
-        buf = torch.empty(B + B * L * 2, device=dev)
-        ms = timed(lambda: (ops._launch_fwdbwd(p, tc, err, None, M, 0, wl["sigma"], 1, 0, None, None, buf[:B], buf[B:], 0),
-                            ops._finalize(buf[:B], B * M, "sharp", 0.99, 100, buf[B:])))
+        buf = torch.empty(B * L * 2 + B, device=dev)
+        lo3 = torch.empty(3, device=dev)
+        ms = timed(lambda: ops._launch_fwdbwd_loss(p, tc, err, M, wl["sigma"], 1, 0, "sharp", 0.99, 100, None, None,
+                                                   buf[B * L * 2:], buf[:B * L * 2], lo3, 0))
         out[name] = {"prop_per_s": B * M * L / (ms * 1e-3), "ms": ms}
     g = torch.Generator().manual_seed(0)
     L = 64
@@ -526,16 +527,17 @@ def other_configs(uq, ops, dev):
                                          ("shipped_grape_B100_L400_M1000_fwdbwd", (100, 400, 1000, 0.035, 0.07))):
         ps = torch.stack([(torch.rand(Bs, Ls, generator=g) * 2 - 1) * 3.15, tlo + (thi - tlo) * torch.rand(Bs, Ls, generator=g)], -1).to(dev)
         tcs = uq.target_coeffs(torch.eye(2, dtype=torch.complex64, device=dev)[None].expand(Bs, -1, -1).contiguous(), torch.float32)
-        bufs = torch.empty(Bs + Bs * Ls * 2, device=dev)
-        ms = timed(lambda: (ops._launch_fwdbwd(ps, tcs, None, None, Ms, 0, (1.0, 0.05), 1, 0, None, None, bufs[:Bs], bufs[Bs:], 0),
-                            ops._finalize(bufs[:Bs], Bs * Ms, "sharp", 0.99, 100, bufs[Bs:])))
+        bufs = torch.empty(Bs * Ls * 2 + Bs, device=dev)
+        ng = Bs * Ls * 2
+        ms = timed(lambda: (ops._launch_fwdbwd(ps, tcs, None, None, Ms, 0, (1.0, 0.05), 1, 0, None, None, bufs[ng:], bufs[:ng], 0),
+                            ops._finalize(bufs[ng:], Bs * Ms, "sharp", 0.99, 100, bufs[:ng])))
         out[name] = {"prop_per_s": Bs * Ms * Ls / (ms * 1e-3), "ms": ms}
     wl = make_workload("curriculum", dev)
     B, L, M = 512, wl["L"], wl["M"]
     p = wl["pulses"][:B].double().to(dev)
     tc = uq.target_coeffs(wl["U_target"][:B].to(dev), torch.float64)
-    buf = torch.empty(B + B * L * 2, dtype=torch.float64, device=dev)
-    ms = timed(lambda: ops._launch_fwdbwd(p, tc, None, None, M, 0, wl["sigma"], 1, 0, None, None, buf[:B], buf[B:], 0), 3)
+    buf = torch.empty(B * L * 2 + B, dtype=torch.float64, device=dev)
+    ms = timed(lambda: ops._launch_fwdbwd(p, tc, None, None, M, 0, wl["sigma"], 1, 0, None, None, buf[B * L * 2:], buf[:B * L * 2], 0), 3)
     out["c5_slice_fp64_B512_fwdbwd"] = {"prop_per_s": B * M * L / (ms * 1e-3), "ms": ms}
     return out
 
@@ -545,7 +547,7 @@ def _sharded_explicit(uq, ops, p, T, e_local, M, M_total, rank, group, flags):
     import torch.distributed as dist
     tc = uq.target_coeffs(T, p.dtype)
     return ops._FusedPropagateLoss.apply(p, tc, e_local, M, rank * M, M_total, (1.0, 0.05), 0, 0, "sharp", 0.99, 100, flags,
-                                         group, None, None)
+                                         group, None, None, None)
 
 
 if __name__ == "__main__":

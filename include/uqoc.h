@@ -56,6 +56,9 @@ extern "C" {
                                     8 trace coefficients are formed in the kernel prologue (one launch less) */
 #define UQOC_FLAG_SU4_PADE 64u   /* SU(4): per-pulse scaling-and-squaring exponential kernel instead of the default
                                     eigenframe kernel (one real-symmetric eigendecomposition per error sample) */
+#define UQOC_FLAG_NO_FIN (1u << 30) /* fused SU(2) step: partials reduction / exchange / loss as separate launches instead
+                                       of the in-kernel "last block" epilogue */
+#define UQOC_FLAG_NO_FAT (1u << 31) /* packed kernel: no fat (7 x 128-thread, one per SM) blocks for few-target shapes */
 /* tuning overrides (0 = let the library choose): samples per thread (1,2,4) and lanes per
  * sample (1,2,4,8,16,32) of the shared-pulse kernels */
 #define UQOC_FLAG_ST(n) (((unsigned)(n) & 0xFu) << 8)
@@ -90,6 +93,9 @@ int uqoc_su2_target_coeffs(const void* U_target, int64_t B, void* target_c, int 
  * (autograd keeps every (Bm,L,2,2) intermediate instead).
  * ------------------------------------------------------------------------ */
 int64_t uqoc_su2_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags);
+/* The first 256 bytes of a workspace hold the ticket counter of the in-kernel epilogue: they must be ZERO when the
+ * buffer is first handed to the library (which leaves them zero again at the end of every call), and one workspace
+ * must not be shared by calls that can run concurrently (one per stream). */
 
 /* ------------------------------------------------------------------------
  * Fused forward+backward for the trainer's Monte-Carlo step
@@ -119,9 +125,10 @@ int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, c
 
 /* ------------------------------------------------------------------------
  * Single-GPU training step in one call: uqoc_su2_fwdbwd followed by the loss epilogue of
- * uqoc_loss_finalize (n_total = B*M), with the partials reduction and the epilogue fused into one
- * kernel when a target's samples are split over blocks.  The whole of trainer.py:80-90 between the
- * model forward and the model backward in at most two launches.  loss_out = {loss, Fbar, dloss/dFbar};
+ * uqoc_loss_finalize (n_total = B*M).  While the partial rows fit one block's bandwidth (few targets, e.g.
+ * BASELINE config 3) the partials reduction, the loss and the chain factor run in the LAST block of the fused
+ * kernel (one launch for the whole of trainer.py:80-90 between the model forward and the model backward);
+ * otherwise in one or two follow-up launches.  loss_out = {loss, Fbar, dloss/dFbar};
  * G comes back already scaled (= d loss / d pulses).
  * ------------------------------------------------------------------------ */
 int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* err,
@@ -157,6 +164,19 @@ int uqoc_su2_fwdbwd_peer(const void* pulses, const void* target_c, const void* e
                          void* workspace, int64_t workspace_bytes,
                          int rank, int world, const uint64_t* peer_data, const uint64_t* peer_flags, uint32_t epoch,
                          int dtype, unsigned flags, void* stream);
+
+/* Same step with the loss epilogue of uqoc_loss_finalize folded in (n_total = B * M_global): for small exchange
+ * vectors the whole multi-GPU step is ONE launch -- the last block of the fused kernel reduces the partials, pushes
+ * them to the peers, waits for theirs, sums in rank order, evaluates the loss and scales G.  loss_out as in
+ * uqoc_su2_fwdbwd_loss; every rank ends with bit-identical {loss, Fsum, G}. */
+int uqoc_su2_fwdbwd_peer_loss(const void* pulses, const void* target_c, const void* err,
+                              int64_t B, int64_t L, int64_t M, int64_t j0, int64_t M_global,
+                              double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                              int loss_kind, double tau, double k,
+                              void* F_out, void* err_out, void* Fsum, void* G, void* loss_out,
+                              void* workspace, int64_t workspace_bytes,
+                              int rank, int world, const uint64_t* peer_data, const uint64_t* peer_flags, uint32_t epoch,
+                              int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
  * Forward only with pulses shared per target (trainer.py:113-120 evaluate;

@@ -121,3 +121,48 @@ def forward_fidelity(pulses, U_target, error, M, generator=generator_tree):
         p_mc = pulses.repeat_interleave(M, dim=0)
         t_mc = U_target.repeat_interleave(M, dim=0)
         return fidelity(generator(p_mc, error), t_mc, 1)
+
+
+# ----------------------------------------------------------------------------- two-qubit SU(4) cross-oracle
+# NOT in the reference (README.md:86,122 promise train/two_qubit/ only).  SURVEY.md §8a A9 prescribes the oracle:
+# torch.linalg.matrix_exp + the SCORE.py:131-142 tree on the builder-defined Hamiltonian (include/uqoc.h)
+#   H = 1/2 [cos phi1 XI + sin phi1 YI + cos phi2 IX + sin phi2 IY + delta1 ZI + delta2 IZ + J ZZ],
+#   U_k = exp(-i H_k tau_k (1 + eps)),
+# in complex128 with autograd gradients.  Parity UNPINNED by the reference; this is a second, independent formulation
+# next to oracle/uqoc_oracle.py::su4_* (numpy eigendecomposition) -- tests/golden/su4_cross.npz is generated from it.
+def su4_generator_tree(pulses: torch.Tensor, error: torch.Tensor, J: float = 1.0) -> torch.Tensor:
+    """pulses (Bm, L, 3) [phi1, phi2, tau], error (3, Bm) [delta1; delta2; eps] -> (Bm, 4, 4), following the op
+    sequence of SCORE.py:116-142 (element-wise Hamiltonian build, matrix_exp, log2(L) batched-matmul tree)."""
+    if pulses.ndim != 3 or pulses.shape[-1] != 3:
+        raise ValueError("'pulses' must have shape (B, L, 3)")
+    Bm = pulses.shape[0]
+    cdtype = torch.complex64 if pulses.dtype == torch.float32 else torch.complex128
+    s = _paulis(cdtype, pulses.device)
+    I2, X, Y, Z = s[0], s[1], s[2], s[3]
+    XI, YI, ZI = torch.kron(X, I2), torch.kron(Y, I2), torch.kron(Z, I2)
+    IX, IY, IZ = torch.kron(I2, X), torch.kron(I2, Y), torch.kron(I2, Z)
+    ZZ = torch.kron(Z, Z)
+    p1, p2, tau = pulses[..., 0], pulses[..., 1], pulses[..., 2]
+    d1, d2, eps = error[0], error[1], error[2]
+    e4 = lambda v: v[..., None, None]
+    ham = e4(torch.cos(p1)) * XI + e4(torch.sin(p1)) * YI + e4(torch.cos(p2)) * IX + e4(torch.sin(p2)) * IY
+    ham = ham + d1[:, None, None, None] * ZI + d2[:, None, None, None] * IZ + J * ZZ
+    ham = 0.5 * ham
+    steps = torch.linalg.matrix_exp(-1j * ham * e4(tau) * (1 + eps)[:, None, None, None])
+    eye = torch.eye(4, dtype=cdtype, device=pulses.device).expand(Bm, 1, 4, 4)
+    level = steps
+    while level.size(1) > 1:
+        if level.size(1) % 2 == 1:
+            level = torch.cat([level, eye], dim=1)
+        level = level[:, 1::2] @ level[:, 0::2]
+    return level[:, 0]
+
+
+def su4_train_step(pulses, U_target, error, M, J=1.0, loss="sharp", tau=0.99, k=100):
+    """trainer.py:80-88 with the SU(4) generator (num_qubits = 2): returns (loss (), F (B*M,), U (B*M, 4, 4)); call
+    ``loss.backward()`` for d loss / d pulses on the ``pulses`` leaf."""
+    p_mc = pulses.repeat_interleave(M, dim=0)
+    t_mc = U_target.repeat_interleave(M, dim=0)
+    U = su4_generator_tree(p_mc, error, J)
+    F = fidelity(U, t_mc, 2)
+    return loss_value(F, loss, tau, k), F, U

@@ -37,3 +37,35 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+# ---- measured accuracy next to every FP32 bound ("stop hiding tolerances"): tests call record_measured();
+# the numbers are printed in the terminal summary and written to gpurun_out/measured_tolerances.json (copied to profiles/)
+_MEASURED = []
+
+
+def record_measured(test: str, what: str, value: float, bound: float, note: str = "") -> float:
+    _MEASURED.append({"test": test, "what": what, "measured": float(value), "bound": float(bound), "note": note})
+    return value
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    if not _MEASURED:
+        return
+    import json
+    worst = {}
+    for m in _MEASURED:
+        key = (m["test"], m["what"])
+        if key not in worst or m["measured"] > worst[key]["measured"]:
+            worst[key] = m
+    rows = sorted(worst.values(), key=lambda m: (m["test"], m["what"]))
+    terminalreporter.write_line("measured accuracy (worst case per test / quantity):")
+    for m in rows:
+        terminalreporter.write_line(f"  {m['test']:58s} {m['what']:10s} measured {m['measured']:.2e}  bound {m['bound']:.1e}  {m['note']}")
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "measured_tolerances.json"), "w") as fh:
+            json.dump(rows, fh, indent=1)
+    except OSError:
+        pass

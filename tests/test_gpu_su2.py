@@ -14,7 +14,7 @@ import torch
 import universal_quantum_optimal_control_b200 as uq
 from oracle import uqoc_oracle as orc
 from oracle import torch_port as tp
-from conftest import load_golden
+from conftest import load_golden, record_measured
 
 pytestmark = pytest.mark.gpu
 
@@ -39,6 +39,14 @@ def _fused(pulses, U_target, error, M, dtype, loss="sharp", flags=0, fast=False,
     val.backward()
     return (val.item(), p.grad.detach().cpu().numpy().astype(np.float64),
             None if F_out is None else F_out.cpu().numpy().astype(np.float64), mean_fid.cpu().numpy().astype(np.float64))
+
+
+def _fscale(T, B, M):
+    """Natural scale of F = (|Tr(U^dagger T)|^2 + 2)/6 for a general complex target: |Tr|^2 <= 2 |T|_F^2, which is 4 for
+    a unitary T.  The FP32 bound of BASELINE.json (1e-5 abs on F in [1/3, 1]) is applied relative to
+    max(1, |T|_F^2 / 2) per target -- 1 for every unitary target -- instead of being loosened by hand."""
+    n2 = (np.abs(np.asarray(T).reshape(B, -1)) ** 2).sum(1) / 2.0
+    return np.repeat(np.maximum(1.0, n2), M)
 
 
 def _relerr(a, b):
@@ -85,8 +93,12 @@ def test_ragged_lengths(L, dtype):
 def test_general_complex_target(dtype):
     g = load_golden("general_target.npz")
     val, grad, F, _ = _fused(g["pulses"], g["U_target"], g["error"], int(g["M"]), dtype)
-    tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (2e-5, F32_TOL_G)   # |tr| up to ~3 here
-    assert np.abs(F - g["F64"]).max() < tolF
+    tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (F32_TOL_F, F32_TOL_G)
+    dF = (np.abs(F - g["F64"]) / _fscale(g["U_target"], 2, int(g["M"]))).max()     # non-unitary target: |T|_F^2 / 2 ~ 2
+    if dtype == torch.float32:
+        record_measured("test_general_complex_target", "dF/scale", dF, tolF, "non-unitary T, L=64")
+        record_measured("test_general_complex_target", "rel dG", _relerr(grad, g["grad64"]), tolG)
+    assert dF < tolF
     assert _relerr(grad, g["grad64"]) < tolG
 
 
@@ -119,8 +131,12 @@ def test_every_launch_shape_matches_oracle(st, lps, nopk, wps, dtype):
     for splits in (0, 1, 3):
         flags = uq.tuning_flags(st=st, lps=lps, splits=splits, no_packed=nopk, wps=wps)
         val, grad, F, _ = _fused(pulses, T, err, M, dtype, flags=flags)
-        tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (3e-5, F32_TOL_G)
-        assert np.abs(F - want_F).max() < tolF, (st, lps, splits)
+        tolF, tolG = (1e-11, 1e-11) if dtype == torch.float64 else (F32_TOL_F, F32_TOL_G)
+        dF = (np.abs(F - want_F) / _fscale(T, B, M)).max()            # random complex T: |T|_F^2 / 2 up to ~5
+        if dtype == torch.float32:
+            record_measured("test_every_launch_shape_matches_oracle", "dF/scale", dF, tolF, f"st={st} lps={lps} wps={wps}")
+            record_measured("test_every_launch_shape_matches_oracle", "rel dG", _relerr(grad, want_g), tolG)
+        assert dF < tolF, (st, lps, splits)
         assert _relerr(grad, want_g) < tolG, (st, lps, splits)
         assert abs(val - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
 
@@ -141,8 +157,13 @@ def test_wide_angle_range_negative_and_multi_turn(st, lps, nopk, wps, notab):
     want_l, want_g, want_F = orc.loss_and_grad(pulses.astype(np.float64), T, err.astype(np.float64), M, "infidelity")
     flags = uq.tuning_flags(st=st, lps=lps, no_packed=nopk, wps=wps, no_table=notab)
     val, grad, F, _ = _fused(pulses, T, err, M, torch.float32, loss="infidelity", flags=flags)
-    # angles reach ~60 rad here: the FP32 rounding of h itself (6e-8 relative) is 4e-6 rad per pulse
-    assert np.abs(F - want_F).max() < 1e-4
+    # Outside BASELINE's tolerance domain on purpose: angles reach ~60 rad here, so the FP32 rounding of the INPUT angle
+    # h itself (6e-8 relative) is 4e-6 rad per pulse -- the bound is input conditioning, not kernel error (the FP64
+    # kernel on the same inputs is checked to 1e-11 below); measured values are recorded
+    dF = (np.abs(F - want_F) / _fscale(T, B, M)).max()
+    record_measured("test_wide_angle_range_negative_and_multi_turn", "dF/scale", dF, 3e-5, "angles to 60 rad: FP32 input rounding")
+    record_measured("test_wide_angle_range_negative_and_multi_turn", "rel dG", _relerr(grad, want_g), 5e-4, "angles to 60 rad")
+    assert dF < 3e-5
     assert _relerr(grad, want_g) < 5e-4
     val64, grad64, F64, _ = _fused(pulses, T, err, M, torch.float64, loss="infidelity", flags=uq.tuning_flags(st=min(st, 2), lps=lps))
     assert np.abs(F64 - want_F).max() < 1e-11
@@ -198,10 +219,14 @@ def test_generator_adapter_matches_golden_and_grid_layout():
 def test_score_composite_pulses(key):
     g = load_golden("score_pulses.npz")
     K = g["probe"].shape[1]
-    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 6e-5)):   # L ~ 400, angles up to ~12 rad: ref FP32 noise is 2e-5
+    # FP32: the pulse angles are given in float32 (util.py:64-112) with rotations up to ~12 rad over L ~ 400 segments;
+    # the reference's own complex64 path is 2e-5 off its complex128 path on these pulses
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 2e-5)):
         pulse = _t(g[f"{key}_pulse"], dtype)
         U = uq.batched_unitary_generator(pulse.expand(K, -1, -1), _t(g["probe"], dtype))
         F = uq.fidelity(U, _t(g[f"{key}_U_target"]).expand(K, -1, -1), 1).cpu().numpy()
+        if dtype == torch.float32:
+            record_measured("test_score_composite_pulses", "dF", np.abs(F - g[f"{key}_F64"]).max(), tol, f"{key}: L={pulse.shape[0]}")
         assert np.abs(F - g[f"{key}_F64"]).max() < tol
         assert F[0] > 1 - 1e-4 and F[1] > 0.998 and F[2] > 0.995
 
@@ -408,7 +433,10 @@ def test_long_pulse_train_uses_opt_in_shared_memory_and_rejects_beyond():
         val, grad, F, _ = _fused(pulses, T, err, M, torch.float64, flags=uq.tuning_flags(st=min(st, 2)))
         assert np.abs(F - want_F).max() < 1e-11 and _relerr(grad, want_g) < 1e-10
         val, grad, F, _ = _fused(pulses.astype(np.float32), T, err.astype(np.float32), M, torch.float32, flags=uq.tuning_flags(st=st))
-        assert np.abs(F - want_F).max() < 5e-5 and _relerr(grad, want_g) < 1e-3     # 1500 pulses of FP32 rounding
+        # 1500 pulses: 6x the longest BASELINE train; FP32 rounding accumulates ~sqrt(L) -- measured values recorded
+        record_measured("test_long_pulse_train", "dF", np.abs(F - want_F).max(), 2e-5, f"L=1500 st={st}")
+        record_measured("test_long_pulse_train", "rel dG", _relerr(grad, want_g), 1e-4, f"L=1500 st={st}")
+        assert np.abs(F - want_F).max() < 2e-5 and _relerr(grad, want_g) < 1e-4
     big = torch.zeros(1, 60000, 2, device=DEV)
     with pytest.raises(UqocError, match="shared memory"):
         uq.fused_propagate_loss(big.requires_grad_(True), _t(T[:1]), monte_carlo=8)
@@ -442,7 +470,10 @@ def test_default_plan_every_regime_matches_oracle(B, L, M):
     err = np.stack([rng.normal(0, 1, B * M), rng.normal(0, 0.05, B * M)]).astype(np.float32)
     want_l, want_g, want_F = orc.loss_and_grad(pulses.astype(np.float64), T, err.astype(np.float64), M, "nll")
     val, grad, F, mf = _fused(pulses, T, err, M, torch.float32, loss="nll")
-    assert np.abs(F - want_F).max() < 3e-5                       # general complex T: |tr|^2 up to ~20, not 4
+    dF = (np.abs(F - want_F) / _fscale(T, B, M)).max()            # general complex T: |T|_F^2 / 2 up to ~5
+    record_measured("test_default_plan_every_regime_matches_oracle", "dF/scale", dF, F32_TOL_F, f"B={B} L={L} M={M}")
+    record_measured("test_default_plan_every_regime_matches_oracle", "rel dG", _relerr(grad, want_g), F32_TOL_G)
+    assert dF < F32_TOL_F
     assert _relerr(grad, want_g) < F32_TOL_G
     assert abs(val - want_l) < 1e-4 * max(1.0, abs(want_l))
     assert np.abs(mf - want_F.reshape(B, M).mean(1)).max() < 1e-5

@@ -62,11 +62,11 @@ def _worker(rank, world, port, philox, ret):
         full = np.stack([rng.normal(0, 1, B * M_total), rng.normal(0, 0.05, B * M_total)])
         err = shard_errors(torch.from_numpy(full), B, M_total, j0, M).numpy()
     Fsum, G, _ = orc.fidelity_sum_and_grad(pulses, T, err, M)                         # stands in for the kernel
-    buf = torch.from_numpy(np.concatenate([Fsum, G.reshape(-1)]))
+    buf = torch.from_numpy(np.concatenate([G.reshape(-1), Fsum]))                     # the product's [G | Fsum] layout
     dist.all_reduce(buf)                                                              # the one exchange step
-    Fbar = buf[:B].sum().item() / (B * M_total)
+    Fbar = buf[B * L * 2:].sum().item() / (B * M_total)
     val, dval = orc.loss_and_dloss(Fbar, "sharp")
-    grad = (dval / (B * M_total)) * buf[B:].numpy().reshape(B, L, 2)
+    grad = (dval / (B * M_total)) * buf[:B * L * 2].numpy().reshape(B, L, 2)
     if rank == 0:
         err_all = orc.philox_errors(B, M_total, 0.7, 0.05, 42, 1) if philox else full
         want_l, want_g, _ = orc.loss_and_grad(pulses, T, err_all, M_total, "sharp")

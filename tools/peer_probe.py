@@ -17,7 +17,7 @@ g = torch.Generator().manual_seed(0)
 pulses = torch.stack([(torch.rand(B, L, generator=g) * 2 - 1) * 3.15, 0.035 + 0.035 * torch.rand(B, L, generator=g)], -1).to(dev)
 tc = torch.zeros(B, 8, device=dev); tc[:, 0] = 2.0
 buf = torch.empty(B + B * L * 2, device=dev)
-Fsum, G = buf[:B], buf[B:]
+G, Fsum = buf[:B * L * 2], buf[B * L * 2:]
 px = uq.PeerExchange(dist.group.WORLD, B, L, 2, torch.float32, dev)
 M_total = M * world
 

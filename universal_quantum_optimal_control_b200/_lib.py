@@ -12,6 +12,8 @@ LIB_PATH = os.environ.get("UQOC_LIB") or os.path.join(HERE, "lib", "libuqoc.so")
 
 F32, F64 = 0, 1
 FLAG_FAST_SINCOS = 1
+FLAG_NO_FIN = 1 << 30          # UQOC_FLAG_NO_FIN: no in-kernel epilogue (separate reduction / loss launches)
+FLAG_NO_FAT = 1 << 31          # UQOC_FLAG_NO_FAT: no fat blocks for few-target shapes
 LOSS_KINDS = {"sharp": 0, "nll": 1, "infidelity": 2, "none": 3}
 
 _lib = None
@@ -32,6 +34,9 @@ SIGNATURES = {
     "uqoc_su2_fwdbwd_peer": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
                                     _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.c_uint32, _int, _uint, _vp]),
+    "uqoc_su2_fwdbwd_peer_loss": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64, _int, _dbl, _dbl,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint64), C.c_uint32, _int, _uint, _vp]),
     "uqoc_su2_fwdbwd_loss": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64, _int, _dbl, _dbl,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_su2_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,

@@ -117,10 +117,30 @@ static Su2Plan make_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fl
     if (fsp) splits = fsp < plan.n_tiles ? fsp : plan.n_tiles;
     plan.splits = (int)splits;
     plan.table = plan.packed && !(flags & UQOC_FLAG_FAST_SINCOS) && !(flags & UQOC_FLAG_NO_TABLE);
-    plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd, (flags & UQOC_FLAG_NO_TABLE) ? 0 : 1024)
-                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, plan.wps, plan.st, bwd, plan.table) : su2_smem_bytes<float>(lps, plan.C, bwd));
+    // fat block (few targets, train split over warps): one 7 x 128-thread block per SM; its virtual blocks are sample-tile
+    // streams of the same target that share the staged pulse train / table, and the target leaves one partial row per
+    // block (148 instead of 1024 at BASELINE config 3), few enough for the in-kernel epilogue
+    plan.vb = 1;
+    plan.cps = plan.splits;
+    if (plan.packed && plan.table && bwd && plan.wps == 4 && plan.st == 2 && !fsp && !(flags & UQOC_FLAG_NO_FAT) &&
+        B * 2 <= sms && plan.n_tiles >= 2 * kX2FatVB) {
+        int64_t cps = sms / B;
+        const int64_t need = (plan.n_tiles + kX2FatVB - 1) / kX2FatVB;
+        if (cps > need) cps = need;
+        plan.vb = kX2FatVB;
+        plan.cps = (int)cps;
+        plan.splits = (int)cps * kX2FatVB;
+    }
+    const int fin_thr = bwd ? kThreads * plan.vb : 0;
+    plan.fin = false;                                   // decided per call (su2_run)
+    plan.smem = (dtype == UQOC_F64) ? su2_smem_bytes<double>(lps, plan.C, bwd, (flags & UQOC_FLAG_NO_TABLE) ? 0 : 1024, bwd)
+                                    : (plan.packed ? su2_x2_smem_bytes(plan.C, plan.wps, plan.st, bwd, plan.table, plan.vb, fin_thr)
+                                                   : su2_smem_bytes<float>(lps, plan.C, bwd, 0, bwd));
     return plan;
 }
+
+// workspace layout: [ticket area | G_part (cps x B*L*2) | Fsum_part (cps x B)]
+constexpr int64_t kTicketBytes = 256;
 
 // ------------------------------------------------------------------ small kernels
 template <typename T>
@@ -174,6 +194,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const T* __restrict_
                                                             T* __restrict__ loss_out) {
     __shared__ double red[256];
     __shared__ double s_scale;
+    grid_dependency_wait();
     double acc = 0.0;
     for (int i = threadIdx.x; i < B; i += 256) acc += (double)Fsum[i];
     red[threadIdx.x] = acc;
@@ -367,39 +388,66 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
                    unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr,
                    const LossSpec* ls = nullptr, const PeerSpec* peer = nullptr) {
-    const Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
+    Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
+    UQOC_CHECK_ARG((int64_t)B * plan.cps <= 0x7fffffffLL, "grid too large: %lld blocks", (long long)(B * plan.cps));
+    UQOC_CHECK_ARG((flags & UQOC_FLAG_RNG_FROM_DEVICE) || offset <= 0xffffffffULL,
+                   "Philox offset must be < 2^32 (it is one 32-bit counter word), got %llu", (unsigned long long)offset);
     Su2Params<T> p;
+    memset(&p, 0, sizeof(p));
     p.pulses = (const T*)pulses;
     p.target_c = (const T*)target_c;
     p.err = (const T*)err;
     p.weight = (const T*)weight;
     p.B = (int)B; p.L = (int)L; p.M = (int)M;
-    p.n_tiles = plan.n_tiles; p.splits = plan.splits; p.C = plan.C;
+    p.n_tiles = plan.n_tiles; p.splits = plan.splits; p.cps = plan.cps; p.C = plan.C;
     p.j0 = j0;
     p.sig_d = (T)sig_d; p.sig_e = (T)sig_e;
-    p.seed = seed; p.offset = (unsigned)offset;
+    p.seed = seed; p.offset = offset;
     p.rng_dev = (flags & UQOC_FLAG_RNG_FROM_DEVICE) ? (const unsigned long long*)(uintptr_t)seed : nullptr;
     p.U_out = (T*)U_out; p.F_out = (T*)F_out; p.err_out = (T*)err_out;
     p.grid_ne = grid_ne; p.sig_tab = (const T*)sig_tab;
     p.raw_target = (flags & UQOC_FLAG_RAW_TARGET) ? 1 : 0;
     const int64_t n_g = bwd ? B * L * 2 : 0;
-    if (plan.splits > 1) {
-        const int64_t need = (int64_t)plan.splits * (B + n_g) * (int64_t)sizeof(T);
-        if (workspace == nullptr || workspace_bytes < need) {
-            set_error("workspace too small: need %lld bytes, got %lld", (long long)need, (long long)workspace_bytes);
+    const int64_t part_bytes = plan.cps > 1 ? (int64_t)plan.cps * (B + n_g) * (int64_t)sizeof(T) : 0;
+    if (plan.cps > 1) {
+        if (workspace == nullptr || workspace_bytes < kTicketBytes + part_bytes) {
+            set_error("workspace too small: need %lld bytes, got %lld", (long long)(kTicketBytes + part_bytes), (long long)workspace_bytes);
             return UQOC_E_WORKSPACE;
         }
-        p.Fsum_part = (T*)workspace;
-        p.G_part = (T*)workspace + (size_t)plan.splits * B;
+        p.G_part = (T*)((char*)workspace + kTicketBytes);          // rows 16-byte aligned when B*L is even
+        p.Fsum_part = p.G_part + (size_t)plan.cps * n_g;
     } else {
         p.Fsum_part = (T*)Fsum;
         p.G_part = (T*)G;
+    }
+    // in-kernel epilogue: the last block reduces the partials, exchanges them with the peers and applies the loss
+    const bool want_fin = bwd && Fsum != nullptr && (ls != nullptr || peer != nullptr || plan.cps > 1);
+    plan.fin = want_fin && !(flags & UQOC_FLAG_NO_FIN) && workspace != nullptr && workspace_bytes >= kTicketBytes &&
+               ((uintptr_t)workspace % 16 == 0) && ((uintptr_t)G % (4 * sizeof(T)) == 0) &&
+               su2_fin_supported(B, L, plan.cps, (plan.packed ? kThreads * plan.vb : kThreads));
+    if (plan.fin) {
+        p.fin.ticket = (unsigned*)workspace;
+        p.fin.Fsum = (T*)Fsum;
+        p.fin.G = (T*)G;
+        p.fin.kind = -1;
+        if (ls != nullptr) {
+            p.fin.kind = ls->kind; p.fin.n_total = ls->n_total; p.fin.tau = ls->tau; p.fin.k = ls->k;
+            p.fin.loss_out = (T*)ls->loss_out;
+        }
+        if (peer != nullptr) {
+            for (int q = 0; q < peer->world; ++q) {
+                p.fin.pp.data[q] = (T*)(uintptr_t)peer->data[q];
+                p.fin.pp.flags[q] = (unsigned*)(uintptr_t)peer->flags[q];
+            }
+            p.fin.pp.rank = peer->rank; p.fin.pp.world = peer->world; p.fin.pp.epoch = peer->epoch;
+            p.fin.pp.n_pad = (n_g + B + 31) / 32 * 32;
+        }
     }
     int rc;
     if (dtype == UQOC_F64) rc = (flags & UQOC_FLAG_NO_TABLE) ? su2_launch<T, SC_LIBM>(p, plan, bwd, stream) : su2_launch<T, SC_TABLE>(p, plan, bwd, stream);
     else if (flags & UQOC_FLAG_FAST_SINCOS) rc = su2_launch<T, SC_MUFU>(p, plan, bwd, stream);
     else rc = su2_launch<T, SC_POLY>(p, plan, bwd, stream);
-    if (rc != 0) return rc;
+    if (rc != 0 || plan.fin) return rc;
     if (peer != nullptr) {
         PeerParams<T> pp;
         for (int q = 0; q < peer->world; ++q) {
@@ -413,19 +461,21 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
         const long long cap = (long long)sm_count() * 2;          // 1024-thread blocks: 2 resident per SM
         if (blocks > cap) blocks = cap;
         if (blocks > kPeerMaxBlocks) blocks = kPeerMaxBlocks;
-        su2_reduce_exchange<T, 32><<<(unsigned)blocks, 1024, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, pp,
-                                                                        (T*)Fsum, (T*)G);
-        return launch_status("su2_reduce_exchange");
-    }
-    if (plan.splits > 1 && (Fsum != nullptr || n_g > 0)) {
-        if (ls != nullptr && (int64_t)plan.splits * B <= 65536 && Fsum != nullptr) {
+        launch_dependent(su2_reduce_exchange<T, 32>, (unsigned)blocks, 1024, 0, stream, (const T*)p.Fsum_part, (const T*)p.G_part,
+                         plan.cps, (int)B, (long long)n_g, pp, (T*)Fsum, (T*)G);
+        rc = launch_status("su2_reduce_exchange");
+        if (rc) return rc;
+    } else if (plan.cps > 1 && (Fsum != nullptr || n_g > 0)) {
+        // few outputs: ONE kernel reduces, evaluates the loss (every block redundantly, from all cps x B partial sums) and
+        // scales; many outputs: the redundant part dominates, two dependent-launched kernels are faster (measured)
+        if (ls != nullptr && (int64_t)plan.cps * B <= 4096 && (n_g + B + 31) / 32 <= 2 * (int64_t)sm_count() && Fsum != nullptr) {
             const long long n = n_g + B;
-            su2_reduce_finalize<T><<<(unsigned)((n + 31) / 32), 1024, 0, stream>>>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g,
-                                                                                ls->n_total, ls->kind, ls->tau, ls->k, (T*)Fsum,
-                                                                                (T*)G, (T*)ls->loss_out);
+            launch_dependent(su2_reduce_finalize<T>, (unsigned)((n + 31) / 32), 1024, 0, stream, (const T*)p.Fsum_part,
+                             (const T*)p.G_part, plan.cps, (int)B, (long long)n_g, ls->n_total, ls->kind, ls->tau, ls->k, (T*)Fsum,
+                             (T*)G, (T*)ls->loss_out);
             return launch_status("su2_reduce_finalize");
         }
-        launch_reduce_partials<T>(p.Fsum_part, p.G_part, plan.splits, (int)B, n_g, (T*)Fsum, (T*)G, stream);
+        launch_reduce_partials<T>(p.Fsum_part, p.G_part, plan.cps, (int)B, n_g, (T*)Fsum, (T*)G, stream);
         rc = launch_status("su2_reduce_partials");
         if (rc) return rc;
     }
@@ -478,10 +528,11 @@ int uqoc_su2_target_coeffs(const void* U_target, int64_t B, void* target_c, int 
 
 int64_t uqoc_su2_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags) {
     if (B < 1 || L < 1 || M < 1) return 0;
-    const Su2Plan plan = make_plan(B, L, M, dtype, flags, true);
-    if (plan.splits <= 1) return 0;
     const int64_t esz = dtype == UQOC_F64 ? 8 : 4;
-    return (int64_t)plan.splits * (B + B * L * 2) * esz;
+    const Su2Plan pb = make_plan(B, L, M, dtype, flags, true), pf = make_plan(B, L, M, dtype, flags, false);
+    const int64_t nb = pb.cps > 1 ? (int64_t)pb.cps * (B + B * L * 2) * esz : 0;      // fused fwd+bwd: [Fsum | G] rows
+    const int64_t nf = pf.cps > 1 ? (int64_t)pf.cps * B * esz : 0;                    // forward only: Fsum rows
+    return kTicketBytes + (nb > nf ? nb : nf);
 }
 
 int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
@@ -522,6 +573,30 @@ int uqoc_su2_fwdbwd_peer(const void* pulses, const void* target_c, const void* e
                                Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, nullptr, &ps);
     return su2_run<float>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
                           G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, nullptr, &ps);
+}
+
+int uqoc_su2_fwdbwd_peer_loss(const void* pulses, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M,
+                              int64_t j0, int64_t M_global, double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                              int loss_kind, double tau, double k, void* F_out, void* err_out, void* Fsum, void* G,
+                              void* loss_out, void* workspace, int64_t workspace_bytes, int rank, int world,
+                              const uint64_t* peer_data, const uint64_t* peer_flags, uint32_t epoch, int dtype, unsigned flags,
+                              void* stream) {
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && target_c && Fsum && G && loss_out, "pulses, target_c, Fsum, G and loss_out must be non-null");
+    UQOC_CHECK_ARG(loss_kind >= 0 && loss_kind <= 3, "unknown loss kind %d", loss_kind);
+    UQOC_CHECK_ARG(M_global >= M, "M_global (%lld) must be >= M (%lld)", (long long)M_global, (long long)M);
+    UQOC_CHECK_ARG(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world %d/%d (max %d ranks)", rank,
+                   world, kPeerMaxWorld);
+    UQOC_CHECK_ARG(peer_data && peer_flags && epoch != 0, "peer_data, peer_flags must be non-null and epoch non-zero");
+    for (int q = 0; q < world; ++q) UQOC_CHECK_ARG(peer_data[q] && peer_flags[q], "null peer pointer for rank %d", q);
+    PeerSpec ps{rank, world, peer_data, peer_flags, epoch};
+    LossSpec ls{(double)B * (double)M_global, tau, k, loss_kind, loss_out};
+    if (dtype == UQOC_F64)
+        return su2_run<double>(pulses, target_c, err, nullptr, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out,
+                               Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, &ls, &ps);
+    return su2_run<float>(pulses, target_c, err, nullptr, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
+                          G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, &ls, &ps);
 }
 
 int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M,
@@ -644,9 +719,11 @@ int uqoc_loss_finalize(const void* Fsum, int64_t B, double n_total, int loss_kin
     if (blocks < 1) blocks = 1;
     if (blocks > 1184) blocks = 1184;
     if (dtype == UQOC_F64)
-        loss_finalize_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)Fsum, (int)B, n_total, loss_kind, tau, k, (double*)G, G_numel, (double*)loss_out);
+        launch_dependent(loss_finalize_kernel<double>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, (const double*)Fsum, (int)B, n_total,
+                         loss_kind, tau, k, (double*)G, (long long)G_numel, (double*)loss_out);
     else
-        loss_finalize_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)Fsum, (int)B, n_total, loss_kind, tau, k, (float*)G, G_numel, (float*)loss_out);
+        launch_dependent(loss_finalize_kernel<float>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, (const float*)Fsum, (int)B, n_total,
+                         loss_kind, tau, k, (float*)G, (long long)G_numel, (float*)loss_out);
     return launch_status("loss_finalize_kernel");
 }
 

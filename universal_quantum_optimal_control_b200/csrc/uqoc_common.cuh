@@ -259,6 +259,7 @@ struct SampleConst {
     T a2;     // (1+eps) w      : full rotation angle per unit tau
     T r;      // 1/w
     T r2;     // 1/w^2
+    T rd;     // delta/w
     T delta;  // detuning
     T ae;     // (1+eps)/2 = a*r : d h / d tau projected on the axis
     T ap;     // a  * 1024/pi : table index of the half angle per unit tau (packed table kernel)
@@ -276,6 +277,7 @@ __device__ __forceinline__ SampleConst<T> make_sample_const(T delta, T eps) {
     k.a2 = (T)((1.0 + e) * w);
     k.r = (T)r;
     k.r2 = (T)(r * r);
+    k.rd = (T)(d * r);
     k.delta = delta;
     k.ae = (T)(0.5 * (1.0 + e));
     k.ap = (T)(0.5 * (1.0 + e) * w * 325.94932345220167);

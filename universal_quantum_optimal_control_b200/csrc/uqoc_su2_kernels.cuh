@@ -22,6 +22,55 @@ namespace uqoc {
 constexpr int kThreads = 128;  // 4 warps: one per SM sub-partition
 constexpr int kWarps = kThreads / 32;
 
+// ---- programmatic dependent launch: the epilogue kernels (partials reduction, exchange, loss) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so their blocks are scheduled while the fused kernel drains and
+// wait HERE for its completion and memory flush (a no-op for a kernel launched the ordinary way)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---- cross-GPU exchange over NVLink peer memory (uqoc_su2_fwdbwd_peer*) --------------------------------------
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerMaxBlocks = 1024;      // flag row length; grid of su2_reduce_exchange <= this
+
+template <typename T>
+struct PeerParams {
+    T* data[kPeerMaxWorld];               // rank q's exchange buffer as mapped in this process: [2][world][n_pad]
+    unsigned* flags[kPeerMaxWorld];       // rank q's flag buffer: [world][kPeerMaxBlocks]
+    int rank, world;                      // world == 0: no exchange
+    unsigned epoch;
+    long long n_pad;
+};
+
+// ---- in-kernel epilogue ("last block done"): partials reduction [+ peer exchange] [+ loss and chain factor] ----
+// Every block bumps a ticket after its partials are globally visible; the block that draws the last ticket sums the
+// partials in fixed order, optionally exchanges the totals with the peer GPUs, evaluates the loss on the pooled mean
+// fidelity and scales the gradient -- the whole step is ONE launch (BASELINE config 3 is a 45 us kernel; the second
+// and third launches used to cost another 10 us).  Used while the partials fit one block's L2 bandwidth.
+template <typename T>
+struct FinParams {
+    unsigned* ticket;      // zero on entry; atomicInc wraps it back to zero (caller-owned workspace); null: epilogue off
+    T* Fsum;               // (B) final per-target fidelity sums
+    T* G;                  // (B, L, 2) final gradient
+    T* loss_out;           // (3) {loss, Fbar, dloss/dFbar} or null
+    double n_total, tau, k;
+    int kind;              // UQOC_LOSS_* or < 0: reduction (and exchange) only
+    PeerParams<T> pp;
+};
+
 template <typename T>
 struct Su2Params {
     const T* pulses;    // (B, L, 2)
@@ -29,22 +78,24 @@ struct Su2Params {
     const T* err;       // (2, B*M) or nullptr (Philox)
     const T* weight;    // (B*M) or nullptr
     int B, L, M;
-    int n_tiles, splits;
+    int n_tiles, splits;   // splits = sample-tile streams per target (blocks per target x virtual blocks per block)
+    int cps;            // blocks per target: grid = B * cps, one partial [Fsum | G] per block
     int C;              // chunk length (padded to the gradient-buffer depth)
     long long j0;
     T sig_d, sig_e;
     unsigned long long seed;
-    unsigned offset;
+    unsigned long long offset;
     T* U_out;      // (B*M, 2, 2, 2) or nullptr
     T* F_out;      // (B*M) or nullptr
     T* err_out;    // (2, B*M) or nullptr
-    T* Fsum_part;  // [splits][B]
-    T* G_part;     // [splits][B][L][2]
+    T* Fsum_part;  // [cps][B]
+    T* G_part;     // [cps][B][L][2]
     // forward-only sweep modes (visualize/util.py:231-249, :313-326)
     const unsigned long long* rng_dev;   // non-null: {seed, offset} read from device memory (CUDA-graph replay)
     int grid_ne;          // > 0: err = [delta axis (M / grid_ne) | eps axis (grid_ne)], sample j -> (j / ne, j % ne)
     const T* sig_tab;     // non-null: per-target (sigma_delta, sigma_eps) rows for the Philox samples
     int raw_target;       // != 0: target_c holds the raw complex targets (B, 2, 2, 2) (UQOC_FLAG_RAW_TARGET)
+    FinParams<T> fin;
 };
 
 // trace coefficients of target b: Tr(U^dagger T) = (cr + i ci) . q.  Either precomputed rows (uqoc_su2_target_coeffs)
@@ -81,7 +132,7 @@ __device__ __forceinline__ void su2_sample_errors(const Su2Params<T>& p, int b, 
         const T sd = p.sig_tab != nullptr ? p.sig_tab[2 * b] : p.sig_d;
         const T se = p.sig_tab != nullptr ? p.sig_tab[2 * b + 1] : p.sig_e;
         const unsigned long long seed = p.rng_dev != nullptr ? p.rng_dev[0] : p.seed;
-        const unsigned offset = p.rng_dev != nullptr ? (unsigned)p.rng_dev[1] : p.offset;
+        const unsigned offset = (unsigned)(p.rng_dev != nullptr ? p.rng_dev[1] : p.offset);   // host rejects >= 2^32
         philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, seed, offset, sd, se, delta, eps);
     }
 }
@@ -138,16 +189,241 @@ __device__ __forceinline__ Quat<T> qshfl(const Quat<T>& q, int src, int width) {
     return Quat<T>{shfl_t(q.a, src, width), shfl_t(q.b, src, width), shfl_t(q.c, src, width), shfl_t(q.d, src, width)};
 }
 
+__device__ __forceinline__ void su2_loss_eval(double Fbar, int kind, double tau, double k, double& val, double& dval) {
+    if (kind == UQOC_LOSS_SHARP) {
+        const double z = exp(-k * (Fbar - tau));
+        const double lg = log(1.0 + z);
+        val = lg * (1.0 - Fbar);
+        dval = -k * z / (1.0 + z) * (1.0 - Fbar) - lg;
+    } else if (kind == UQOC_LOSS_NLL) {
+        val = -log(Fbar);
+        dval = -1.0 / Fbar;
+    } else if (kind == UQOC_LOSS_INFIDELITY) {
+        val = 1.0 - Fbar;
+        dval = -1.0;
+    } else {
+        val = Fbar;
+        dval = 1.0;
+    }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+
+// 4 consecutive reals through L2 (other blocks' / peers' stores: never the non-coherent L1)
+#ifndef UQOC_FIN_LD
+#define UQOC_FIN_LD 0
+#endif
+__device__ __forceinline__ void ld4cg(const float* p, float (&v)[4]) {
+#if UQOC_FIN_LD == 0
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+#elif UQOC_FIN_LD == 1
+    const float4 t = *reinterpret_cast<const float4*>(p);
+#elif UQOC_FIN_LD == 2
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+#else
+    float4 t;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p));
+#endif
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4cg(const double* p, double (&v)[4]) {
+    const double2 t0 = __ldcg(reinterpret_cast<const double2*>(p)), t1 = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+
+// ---- in-kernel epilogue (FinParams): called by every thread of every block after the block's partial [G | Fsum] row
+// has been written to G_part / Fsum_part.  `scr_raw` = shared scratch of su2_fin_smem_bytes() (the sweeps' shared memory
+// is dead by now).  The output vector is small here (the host enables the epilogue only when n_g / 4 + B <= blockDim.x,
+// n_g % 4 == 0): every output column -- 4 gradient reals or one Fsum -- is owned by ONE thread per part-lane, all of a
+// thread's loads are independent 16-byte L2 loads, the column total stays in registers through the exchange and the
+// loss, and G is written once, already scaled.  Fixed summation order everywhere: bit-reproducible, and with a peer
+// exchange bit-identical on every rank (slots are summed in rank order).
+#ifdef UQOC_FIN_INLINE
+#define UQOC_FIN_ATTR __forceinline__
+#else
+#define UQOC_FIN_ATTR __noinline__     // out of line: keeps the sweeps' register allocation independent of the epilogue
+#endif
+template <typename T>
+__device__ UQOC_FIN_ATTR void su2_block_finalize(const FinParams<T>& f, const T* __restrict__ G_part, const T* __restrict__ Fsum_part,
+                                                 const int parts, const int B, const int L, unsigned char* scr_raw) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double* dred = reinterpret_cast<double*>(scr_raw);                       // [40]: warp sums, scale, flags
+    T* red = reinterpret_cast<T*>(scr_raw + 40 * sizeof(double));            // [nthr][4] part-lane partials
+    T* fsm = red + (size_t)nthr * 4;                                         // [B] per-target fidelity sums
+#ifdef UQOC_FIN_TIMING
+    unsigned long long* stamp = reinterpret_cast<unsigned long long*>(f.ticket) + 2;
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    const unsigned long long ts_enter = now();
+#endif
+    __syncthreads();                                               // the block's partial row is complete ...
+    if (tid == 0) {
+        __threadfence();                                           // ... and (cumulatively) visible device-wide before its
+        const unsigned t = atomicInc(f.ticket, gridDim.x - 1);     // ticket is; the counter wraps to 0 after the last one
+        const bool last = (t == gridDim.x - 1);
+        if (last) __threadfence();
+        dred[39] = last ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (dred[39] == 0.0) return;
+#ifdef UQOC_FIN_TIMING
+    if (tid == 0) { stamp[0] = ts_enter; stamp[1] = now(); }
+#endif
+    const int n_g = B * L * 2, ncol4 = n_g / 4, ncol = ncol4 + B;
+    int Y = nthr / ncol;                                           // part-lanes per column
+    if (Y > parts) Y = parts;
+    const int cpp = nthr / Y;                                      // columns per part-lane (>= ncol)
+    const int y = tid / cpp, cx = tid % cpp;
+    const bool owner = (y == 0) && cx < ncol;                      // holds the column's total from here on
+    // ---- 1. fixed-order sum over the blocks' partial rows
+    T a[4] = {(T)0, (T)0, (T)0, (T)0};
+    if (y < Y && cx < ncol) {
+        if (cx < ncol4) {
+            const T* src = G_part + 4 * cx;
+#pragma unroll 8
+            for (int s = y; s < parts; s += Y) {
+                T v[4];
+                ld4cg(src + (size_t)s * n_g, v);
+                a[0] += v[0]; a[1] += v[1]; a[2] += v[2]; a[3] += v[3];
+            }
+        } else {
+            const T* src = Fsum_part + (cx - ncol4);
+#pragma unroll 8
+            for (int s = y; s < parts; s += Y) a[0] += __ldcg(src + (size_t)s * B);
+        }
+    }
+    if (Y > 1) {
+        st4(red + 4 * (size_t)tid, a);
+        __syncthreads();
+        if (owner) {
+            for (int yy = 1; yy < Y; ++yy) {
+                const T* r = red + 4 * (size_t)(yy * cpp + cx);
+                a[0] += r[0]; a[1] += r[1]; a[2] += r[2]; a[3] += r[3];
+            }
+        }
+    }
+#ifdef UQOC_FIN_TIMING
+    __syncthreads();
+    if (tid == 0) stamp[2] = now();
+#endif
+    // ---- 2. peer exchange: push into slot[rank] of every rank (NVLink stores), flags up, wait, sum in rank order
+    if (f.pp.world > 0) {
+        const size_t set_off = (size_t)(f.pp.epoch & 1u) * f.pp.world * f.pp.n_pad;
+        const size_t col_off = cx < ncol4 ? 4 * (size_t)cx : (size_t)n_g + (cx - ncol4);
+        if (owner) {
+            const size_t o = set_off + (size_t)f.pp.rank * f.pp.n_pad + col_off;
+            for (int q = 0; q < f.pp.world; ++q) {
+                if (cx < ncol4) st4(f.pp.data[q] + o, a);
+                else f.pp.data[q][o] = a[0];
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (tid < f.pp.world) st_release_sys(f.pp.flags[tid] + (size_t)f.pp.rank * kPeerMaxBlocks, f.pp.epoch);
+        if (tid == 0) dred[38] = 0.0;
+        __syncthreads();
+        if (tid < f.pp.world) {
+            const unsigned* fl = f.pp.flags[f.pp.rank] + (size_t)tid * kPeerMaxBlocks;
+            unsigned long long t0 = 0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while ((int)(ld_acquire_sys(fl) - f.pp.epoch) < 0) {   // epochs only grow (mod 2^32); a peer may be one call ahead
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 10000000000ull) {                    // 10 s: a peer never made the matching call
+                    dred[38] = 1.0;                                // -> NaN outputs instead of a hung GPU
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (owner) {
+            const T* mine = f.pp.data[f.pp.rank] + set_off + col_off;
+            a[0] = a[1] = a[2] = a[3] = (T)0;
+            for (int q = 0; q < f.pp.world; ++q) {
+                if (cx < ncol4) {
+                    T v[4];
+                    ld4cg(mine + (size_t)q * f.pp.n_pad, v);
+                    a[0] += v[0]; a[1] += v[1]; a[2] += v[2]; a[3] += v[3];
+                } else {
+                    a[0] += __ldcg(mine + (size_t)q * f.pp.n_pad);
+                }
+            }
+            if (dred[38] != 0.0) a[0] = a[1] = a[2] = a[3] = (T)NAN;
+        }
+    }
+    // ---- 3. per-target sums out; pooled mean fidelity (double, fixed order), loss, chain factor
+    if (owner && cx >= ncol4) {
+        f.Fsum[cx - ncol4] = a[0];
+        fsm[cx - ncol4] = a[0];
+    }
+    T sc = (T)1;
+    if (f.kind >= 0) {
+        __syncthreads();
+        double t = 0.0;
+        for (int i = tid; i < B; i += nthr) t += (double)fsm[i];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if ((tid & 31) == 0) dred[tid >> 5] = t;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < (nthr + 31) / 32; ++w) tot += dred[w];
+            double val, dval;
+            const double Fbar = tot / f.n_total;
+            su2_loss_eval(Fbar, f.kind, f.tau, f.k, val, dval);
+            dred[37] = dval / f.n_total;
+            if (f.loss_out != nullptr) {
+                f.loss_out[0] = (T)val;
+                f.loss_out[1] = (T)Fbar;
+                f.loss_out[2] = (T)dval;
+            }
+        }
+        __syncthreads();
+        sc = (T)dred[37];
+    }
+#ifdef UQOC_FIN_TIMING
+    if (tid == 0) stamp[3] = now();
+#endif
+    if (owner && cx < ncol4) {
+        a[0] *= sc; a[1] *= sc; a[2] *= sc; a[3] *= sc;
+        st4(f.G + 4 * (size_t)cx, a);
+    }
+#ifdef UQOC_FIN_TIMING
+    __syncthreads();
+    if (tid == 0) stamp[4] = now();
+#endif
+}
+// bytes of shared scratch su2_block_finalize needs for a block of `nthr` threads, and the launch shapes it supports
+__host__ __device__ inline size_t su2_fin_smem_bytes(int nthr, size_t elem) { return 40 * sizeof(double) + (size_t)nthr * 5 * elem; }
+__host__ __device__ inline bool su2_fin_supported(long long B, long long L, int parts, int nthr) {
+    const long long n_g = B * L * 2, ncol = n_g / 4 + B;
+    // <= 4 16-byte loads per thread: beyond that one block's pass over the partial rows (measured 11 us for the 148 rows
+    // of BASELINE config 3) loses to a dependent-launched reduction kernel spread over many SMs (5.7 us)
+    return (n_g % 4 == 0) && ncol <= nthr && (long long)parts * ncol <= 4LL * nthr;
+}
+
 // shared-memory footprint (bytes) of one block
 template <typename T>
-__host__ __device__ inline size_t su2_smem_bytes(int LPS, int C, bool bwd, int table_n = 0) {
+__host__ __device__ inline size_t su2_smem_bytes(int LPS, int C, bool bwd, int table_n = 0, bool fin = false) {
     const size_t rows = (size_t)LPS * (C + 1);
     size_t bytes = rows * sizeof(Row4<T>);                             // forward table
     bytes += 2 * (size_t)table_n * sizeof(T);                          // sin/cos table of the table policies
     if (bwd) bytes += rows * sizeof(Row4<T>);                          // backward table
     if (bwd) bytes += (size_t)kWarps * LPS * C * 2 * sizeof(T);        // per-warp gradient accumulators
     bytes += 32 * sizeof(T);                                           // block-reduction scratch
-    return bytes;
+    const size_t fb = fin ? su2_fin_smem_bytes(kThreads, sizeof(T)) : 0;   // in-kernel epilogue (reuses the block's memory)
+    return bytes > fb ? bytes : fb;
 }
 
 template <typename T, int ST, int LPS, int SC, bool BWD>
@@ -419,6 +695,11 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
             for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
             gout[i] = (i & 1) ? tot : tot * (T)0.5;   // d/dphi carries the 1/2 of sin 2h = 2 s c
         }
+        if (p.fin.ticket != nullptr) {
+            __syncthreads();                          // the accumulators are dead: the epilogue reuses shared memory
+            const FinParams<T> fin = p.fin;           // a copy: the kernel parameters themselves stay in the constant bank
+            su2_block_finalize<T>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw);
+        }
     }
 }
 
@@ -434,6 +715,7 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_partials(const T* __restri
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const long long i = (long long)blockIdx.x * 32 + x;
     const long long n_f = (Fsum != nullptr) ? B : 0;
+    grid_dependency_wait();
     T tot = (T)0;
     if (i < n_g) {
 #pragma unroll 8
@@ -457,24 +739,6 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_partials(const T* __restri
 // Every block first recomputes Fbar = sum_{split,b} Fsum_part / n_total with the same fixed-order tree
 // (bit-identical across blocks), evaluates the loss and d loss / d Fbar, then reduces its 32 outputs over
 // the splits and scales them.  Saves one launch per step, which matters at BASELINE config 3 size.
-__device__ __forceinline__ void su2_loss_eval(double Fbar, int kind, double tau, double k, double& val, double& dval) {
-    if (kind == UQOC_LOSS_SHARP) {
-        const double z = exp(-k * (Fbar - tau));
-        const double lg = log(1.0 + z);
-        val = lg * (1.0 - Fbar);
-        dval = -k * z / (1.0 + z) * (1.0 - Fbar) - lg;
-    } else if (kind == UQOC_LOSS_NLL) {
-        val = -log(Fbar);
-        dval = -1.0 / Fbar;
-    } else if (kind == UQOC_LOSS_INFIDELITY) {
-        val = 1.0 - Fbar;
-        dval = -1.0;
-    } else {
-        val = Fbar;
-        dval = 1.0;
-    }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(1024) su2_reduce_finalize(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
                                                             int splits, int B, long long n_g, double n_total, int kind,
@@ -485,6 +749,7 @@ __global__ void __launch_bounds__(1024) su2_reduce_finalize(const T* __restrict_
     __shared__ double fred[1024];
     __shared__ double s_scale;
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    grid_dependency_wait();
     // Fbar: fixed-order strided partial sums + tree
     {
         double a = 0.0;
@@ -541,27 +806,6 @@ __global__ void __launch_bounds__(1024) su2_reduce_finalize(const T* __restrict_
 //   every rank, so all ranks end with bit-identical [G | Fsum].
 // Two slot sets alternate with the epoch (a rank can only be one call ahead of the slowest peer).  The grid is
 // capped at the resident capacity so every waiting block has its remote partner running.
-constexpr int kPeerMaxWorld = 16;
-constexpr int kPeerMaxBlocks = 1024;      // flag row length; grid <= this
-
-template <typename T>
-struct PeerParams {
-    T* data[kPeerMaxWorld];               // rank q's exchange buffer as mapped in this process: [2][world][n_pad]
-    unsigned* flags[kPeerMaxWorld];       // rank q's flag buffer: [world][kPeerMaxBlocks]
-    int rank, world;
-    unsigned epoch;
-    long long n_pad;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 template <typename T, int YL>
 __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange(const T* __restrict__ Fsum_part, const T* __restrict__ G_part,
                                                                int splits, int B, long long n_g, const PeerParams<T> pp,
@@ -572,6 +816,7 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange(const T* __restri
     const long long n = n_g + B;
     const long long n_groups = (n + 31) / 32;
     const size_t set_off = (size_t)(pp.epoch & 1u) * pp.world * pp.n_pad;
+    grid_dependency_wait();
     // ---- phase 1: reduce over the sample-tile partials, push to every rank's slot[rank]
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long i = g * 32 + x;
@@ -638,8 +883,8 @@ inline void launch_reduce_partials(const T* Fsum_part, const T* G_part, int spli
                                    cudaStream_t stream) {
     const long long n = n_g + (Fsum != nullptr ? B : 0);
     const unsigned blocks = (unsigned)((n + 31) / 32);
-    if (splits > 64) su2_reduce_partials<T, 32><<<blocks, 1024, 0, stream>>>(Fsum_part, G_part, splits, B, n_g, Fsum, G);
-    else su2_reduce_partials<T, 8><<<blocks, 256, 0, stream>>>(Fsum_part, G_part, splits, B, n_g, Fsum, G);
+    if (splits > 64) launch_dependent(su2_reduce_partials<T, 32>, blocks, 1024, 0, stream, Fsum_part, G_part, splits, B, n_g, Fsum, G);
+    else launch_dependent(su2_reduce_partials<T, 8>, blocks, 256, 0, stream, Fsum_part, G_part, splits, B, n_g, Fsum, G);
 }
 
 // =============================================================================================
@@ -735,6 +980,9 @@ struct Su2Plan {
     bool packed;   // FP32 only: f32x2 (FFMA2) kernel, two samples per register pair
     int wps;       // packed kernel: warps per sample group (1, or 4 = pulse train split over the block's warps)
     bool table;    // packed kernel: table-lookup sin/cos instead of the polynomial pair
+    int vb;        // packed kernel: virtual blocks per block (kX2FatVB = fat block, one per SM), else 1
+    int cps;       // blocks per target = splits / vb (partial rows per target)
+    bool fin;      // in-kernel epilogue (su2_block_finalize) instead of separate reduction / loss launches
 };
 
 }  // namespace uqoc

@@ -21,14 +21,14 @@ static int su2_launch_one(const Su2Params<T>& p, const Su2Plan& plan, cudaStream
             return UQOC_E_UNSUPPORTED;
         }
     }
-    const unsigned grid = (unsigned)((long long)p.B * plan.splits);
+    const unsigned grid = (unsigned)((long long)p.B * plan.cps);
     kern<<<grid, kThreads, plan.smem, stream>>>(p);
     return launch_status("su2_kernel");
 }
 
-template <int NP, int SC, bool BWD, int WPS>
+template <int NP, int SC, bool BWD, int WPS, int VB>
 static int su2_launch_x2w(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
-    auto kern = su2_kernel_x2<NP, SC, BWD, WPS>;
+    auto kern = su2_kernel_x2<NP, SC, BWD, WPS, VB>;
     if (plan.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) {
@@ -37,14 +37,21 @@ static int su2_launch_x2w(const Su2Params<float>& p, const Su2Plan& plan, cudaSt
             return UQOC_E_UNSUPPORTED;
         }
     }
-    const unsigned grid = (unsigned)((long long)p.B * plan.splits);
-    kern<<<grid, kThreads, plan.smem, stream>>>(p);
+    const unsigned grid = (unsigned)((long long)p.B * plan.cps);
+    kern<<<grid, kThreads * VB, plan.smem, stream>>>(p);
     return launch_status("su2_kernel_x2");
 }
 template <int NP, int SC, bool BWD>
 static int su2_launch_x2(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
-    if (plan.wps == 4) return su2_launch_x2w<NP, SC, BWD, 4>(p, plan, stream);
-    return su2_launch_x2w<NP, SC, BWD, 1>(p, plan, stream);
+    if constexpr (NP == 1 && SC == SC_TABLE && BWD) {
+        if (plan.wps == 4 && plan.vb == kX2FatVB) return su2_launch_x2w<NP, SC, BWD, 4, kX2FatVB>(p, plan, stream);
+    }
+    if (plan.vb != 1) {
+        set_error("internal: fat-block variant not built for this shape");
+        return UQOC_E_UNSUPPORTED;
+    }
+    if (plan.wps == 4) return su2_launch_x2w<NP, SC, BWD, 4, 1>(p, plan, stream);
+    return su2_launch_x2w<NP, SC, BWD, 1, 1>(p, plan, stream);
 }
 
 template <typename T, int SC, bool BWD>

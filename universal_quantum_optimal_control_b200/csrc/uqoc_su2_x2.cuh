@@ -106,48 +106,12 @@ __device__ __forceinline__ void sincos2(F2 h, F2& s, F2& c, int& kb_lo, int& kb_
     }
 }
 
-// Stage-major evaluation for NP independent pairs: consecutive instructions are independent
-// (NP pairs x {sin, cos} Horner chains), which is what keeps the 2-cycle FFMA2 pipe fed from a
+// Stage-major evaluation for NP independent pairs (polynomial / MUFU policies): consecutive instructions are
+// independent (NP pairs x {sin, cos} Horner chains), which is what keeps the 2-cycle FFMA2 pipe fed from a
 // single warp instead of relying on other warps to hide each dependent-issue latency.
-// SC_TABLE: h = k pi/N + r with |r| <= pi/2N (N = 1024).  (sin, cos)(k pi/N) come from a shared-memory
-// table (one LDS.32 per half), the residual is applied to FIRST order, (s, c) = (st + r ct, ct - r st):
-// the angle error is r^3/3 <= 1.2e-9; the norm error r^2/2 <= 1.2e-6 is radial (removed exactly by the
-// final re-normalisation of P_L) and has zero mean because the table is pre-scaled by 1 - (pi/2N)^2/6.
-// 6 FMA-pipe instructions (4 with immediates) instead of 14; the sign (-1)^(k div N) is dropped like in
-// the polynomial path (kb returns k >> 10 so the U_out kernel can track it).
-// FULL: index the full-period table (k mod 2N): the signs of (s, c) are then exact and kb = 0 (the backward
-// sweep looks up the DOUBLE angle 2h this way: cos 2h / sin 2h are what the adjoint rotation needs, and taking
-// them from the table instead of the double-angle identities saves 3 FMA-pipe instructions per pair-step).
-template <int NP, int SC, bool FULL = false>
-__device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
-                                          const float* __restrict__ tsin, const float* __restrict__ tcos) {
-    if constexpr (SC == SC_TABLE) {
-        constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
-        const float MAGIC = 12582912.0f;
-        F2 kf[NP], r[NP], st[NP], ct[NP];
-#pragma unroll
-        for (int u = 0; u < NP; ++u) kf[u] = fma2(h[u], f2b(325.94931f), f2b(MAGIC));
-#pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            const int k0 = __float_as_int(f2lo(kf[u])), k1 = __float_as_int(f2hi(kf[u]));
-            kb[2 * u] = FULL ? 0 : (k0 >> 10);
-            kb[2 * u + 1] = FULL ? 0 : (k1 >> 10);
-            const int i0 = k0 & MASK, i1 = k1 & MASK;
-            st[u] = f2(tsin[i0], tsin[i1]);
-            ct[u] = f2(tcos[i0], tcos[i1]);
-        }
-#pragma unroll
-        for (int u = 0; u < NP; ++u) kf[u] = add2(kf[u], f2b(-MAGIC));
-#pragma unroll
-        for (int u = 0; u < NP; ++u) r[u] = fma2(kf[u], f2b(-0.003067961661145091f), h[u]);
-#pragma unroll
-        for (int u = 0; u < NP; ++u) r[u] = fma2(kf[u], f2b(8.537380524753502e-11f), r[u]);
-#pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            s[u] = fma2(r[u], ct[u], st[u]);
-            c[u] = fma2(neg2(r[u]), st[u], ct[u]);
-        }
-    } else if constexpr (SC == SC_MUFU) {
+template <int NP, int SC>
+__device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP]) {
+    if constexpr (SC == SC_MUFU) {
 #pragma unroll
         for (int u = 0; u < NP; ++u) sincos2<SC>(h[u], s[u], c[u], kb[2 * u], kb[2 * u + 1]);
     } else {
@@ -193,14 +157,37 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
     }
 }
 
-// Table sin/cos of tau * a for NP pairs, from the per-sample table-index slope kap = a * N/pi:
+// Inner-loop formulations under test (tools/variants.sh builds them side by side; the winner becomes the default):
+//   UQOC_X2_FWD_FORM  0 = per-pulse scalars two SAMPLES per register pair, separate sin / cos tables (round 1)
+//                     1 = two COMPONENTS of one sample per pair after the table-index arithmetic, interleaved table
+//   UQOC_X2_BWD_FORM  0 = two samples per pair, separate tables (round 1)
+//                     1 = two samples per pair, table step per sample on the interleaved {sin, cos} pair, re-paired
+//                     2 = (A, W3) component pair + scalar FFMA for the rest
+#ifndef UQOC_X2_FWD_FORM
+#define UQOC_X2_FWD_FORM 1
+#endif
+#ifndef UQOC_X2_BWD_FORM
+#define UQOC_X2_BWD_FORM 0
+#endif
+constexpr int kFwdForm = UQOC_X2_FWD_FORM, kBwdForm = UQOC_X2_BWD_FORM;
+// table entries staged for a kernel: interleaved {sin, cos} pairs and / or separate sin[] / cos[] arrays
+constexpr int x2_tab_il(bool table, bool bwd) {
+    return !table ? 0 : ((bwd && kBwdForm >= 1) ? UQOC_SINCOS_TABLE_LEN : ((kFwdForm == 1) ? kTabN : 0));
+}
+constexpr int x2_tab_sep(bool table, bool bwd) {
+    return !table ? 0 : ((bwd && kBwdForm == 0) ? UQOC_SINCOS_TABLE_LEN : ((kFwdForm == 0) ? kTabN : 0));
+}
+
+// Table sin/cos of tau * a for NP sample pairs, from the per-sample table-index slope kap = a * N/pi:
 //   kf = fma(tau, kap, MAGIC)  (k in the low mantissa bits),  frac = fma(tau, kap, -(kf - MAGIC))  (one rounding),
 //   r = frac * pi/N,  (s, c) = (st + r ct, ct - r st).
-// 6 FMA-pipe instructions; the angle tau*a itself is never formed (the Cody-Waite pair of sincos2_n's table
-// path is replaced by the exact FMA residual).  FULL as in sincos2_n.
+// 6 FMA-pipe instructions; the angle tau*a itself is never formed.  FULL: index the full-period table (k mod 2N), signs
+// exact (the backward sweep looks up the DOUBLE angle 2h this way); otherwise k mod N and the common sign
+// (-1)^(k div N) is dropped (kb returns k >> 10 so the U_out kernel can track it).
+// Separate sin[] / cos[] arrays, two samples per register pair throughout:
 template <int NP, bool FULL>
-__device__ __forceinline__ void sincos2_tab(F2 tau, const F2 (&kap)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
-                                            const float* __restrict__ tsin, const float* __restrict__ tcos) {
+__device__ __forceinline__ void sincos2_tab_sep(F2 tau, const F2 (&kap)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
+                                                const float* __restrict__ tsin, const float* __restrict__ tcos) {
     constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
     const float MAGIC = 12582912.0f;
     F2 kf[NP], fr[NP], st[NP], ct[NP];
@@ -227,17 +214,53 @@ __device__ __forceinline__ void sincos2_tab(F2 tau, const F2 (&kap)[NP], F2 (&s)
         c[u] = fma2(neg2(fr[u]), st[u], ct[u]);
     }
 }
+// INTERLEAVED {sin, cos} table (one LDS.64 per sample); the residual step is done per SAMPLE on the loaded component
+// pair V = (st, ct):  V' = V + (-r) (-ct, st)  -- one FFMA2 whose multiplier rides in the 32-bit broadcast slot and whose
+// other two sources are the SAME register pair (a swap / sign modifier apart).  Outputs V[v] = (sin, cos), v = 2u + half.
+template <int NP, bool FULL>
+__device__ __forceinline__ void sincos2_tab_il(F2 tau, const F2 (&kap)[NP], F2 (&V)[2 * NP], int (&kb)[2 * NP],
+                                               const u64* __restrict__ tsc) {
+    constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
+    const float MAGIC = 12582912.0f;
+    F2 kf[NP], nr[NP], T[2 * NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) kf[u] = fma2(tau, kap[u], f2b(MAGIC));
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+        const int k0 = __float_as_int(f2lo(kf[u])), k1 = __float_as_int(f2hi(kf[u]));
+        kb[2 * u] = FULL ? 0 : (k0 >> 10);
+        kb[2 * u + 1] = FULL ? 0 : (k1 >> 10);
+        T[2 * u].v = tsc[k0 & MASK];
+        T[2 * u + 1].v = tsc[k1 & MASK];
+    }
+#pragma unroll
+    for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
+#pragma unroll
+    for (int u = 0; u < NP; ++u) nr[u] = fma2(tau, kap[u], kf[u]);
+#pragma unroll
+    for (int u = 0; u < NP; ++u) nr[u] = mul2(nr[u], f2b(-0.0030679615757712823f));    // -r = -frac * pi/N
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+        V[2 * u] = fma2(swp2_np(T[2 * u]), f2b(f2lo(nr[u])), T[2 * u]);                 // (st + r ct, ct - r st)
+        V[2 * u + 1] = fma2(swp2_np(T[2 * u + 1]), f2b(f2hi(nr[u])), T[2 * u + 1]);
+    }
+}
 
-// shared memory of one block of the packed kernel (bytes).  C = pulses per chunk, WPS chunks.
-__host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool bwd, bool table) {
+// shared memory of one block of the packed kernel (bytes).  C = pulses per chunk, WPS chunks, VB virtual blocks
+// (128-thread sample groups that share the staged pulse train and the table); fin_threads > 0 reserves the scratch of
+// the in-kernel epilogue (which reuses the block's shared memory from offset 0 once the sweeps are done).
+__host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool bwd, bool table, int vb = 1, int fin_threads = 0) {
     const size_t rows = (size_t)C * wps;
-    size_t bytes = rows * 16;                                     // {cos phi, sin phi, tau, -} rows
+    size_t bytes = 0;
+    bytes += (size_t)(x2_tab_il(table, bwd) + x2_tab_sep(table, bwd)) * 2 * sizeof(float);   // bwd: full period
+    bytes += rows * 16;                                           // {cos phi, sin phi, tau, -} rows
     if (bwd) bytes += rows * 16;                                  // {cos dphi, sin dphi, tau, -} rows
-    if (bwd) bytes += (size_t)kWarps * C * 2 * sizeof(float);     // gradient accumulators (per warp / per chunk)
-    bytes += 32 * sizeof(float);
-    if (table) bytes += 2 * (size_t)(bwd ? UQOC_SINCOS_TABLE_LEN : UQOC_SINCOS_TABLE_N) * sizeof(float);   // bwd: full period
-    if (wps > 1) bytes += (size_t)kWarps * st * 5 * 32 * sizeof(float);   // chunk-product (+ parity) exchange
-    return bytes;
+    size_t per_vb = 32 * sizeof(float);                           // block-reduction scratch
+    if (bwd) per_vb += (size_t)kWarps * C * 2 * sizeof(float);    // gradient accumulators (per warp / per chunk)
+    if (wps > 1) per_vb += (size_t)kWarps * st * 5 * 32 * sizeof(float);   // chunk-product (+ parity) exchange
+    bytes += per_vb * vb;
+    const size_t fin = fin_threads > 0 ? su2_fin_smem_bytes(fin_threads, sizeof(float)) : 0;
+    return bytes > fin ? bytes : fin;
 }
 
 // resident-block hint of the table kernel: 5 blocks/SM (<= 96 registers) measured best (8.33 ms vs 8.50 at 6, 8.37 at 7,
@@ -249,56 +272,96 @@ __host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool
 #define UQOC_X2_FWD_UNROLL 2
 #endif
 constexpr int kX2FwdUnroll = UQOC_X2_FWD_UNROLL;
-constexpr int x2_min_blocks(int NP, int SC, int WPS) { return (WPS == 4 && NP == 1) ? 7 : ((SC == SC_TABLE) ? UQOC_X2_MINB : 1); }
+constexpr int kX2FatVB = 7;           // virtual blocks of the fat-block variant (NP = 1, WPS = 4): 896 threads x 72 registers
+constexpr int x2_min_blocks(int NP, int SC, int WPS, int VB) {
+    return VB > 1 ? 1 : ((WPS == 4 && NP == 1) ? 7 : ((SC == SC_TABLE) ? UQOC_X2_MINB : 1));
+}
+
+// barrier over the 128 threads of one virtual block (VB > 1: named barrier 1 + vb; VB == 1: the block barrier)
+template <int VB>
+__device__ __forceinline__ void vb_sync(int vb) {
+    if constexpr (VB == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(vb + 1), "n"(kThreads) : "memory");
+}
 
 // NP  = sample PAIRS per thread (1 or 2)
 // WPS = warps per sample group.  1: every warp owns its own 32*ST samples and the whole pulse train.
-//       4: the block's four warps share 32*ST samples and each owns a quarter of the pulse train
+//       4: the four warps of a (virtual) block share 32*ST samples and each owns a quarter of the pulse train
 //       (chunk products exchanged through shared memory; the prefix alone seeds every chunk's backward
 //       sweep, see uqoc_su2_kernels.cuh) -- 4x the warps for the same samples, for small sample counts.
-template <int NP, int SC, bool BWD, int WPS>
-__global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kernel_x2(const Su2Params<float> p) {
+// VB  = virtual blocks per block ("fat block", few targets): VB x 128 threads, one block per SM; the virtual blocks
+//       are independent sample-tile streams of the SAME target that share one staged pulse train / trig / table
+//       (staged once per SM instead of once per 128 threads) and whose gradient slices are summed in shared memory,
+//       so a target leaves `cps` partial rows (one per block) instead of `splits`.
+template <int NP, int SC, bool BWD, int WPS, int VB>
+__global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB)) su2_kernel_x2(const Su2Params<float> p) {
     constexpr int ST = 2 * NP;
     constexpr int NB = 8;
-    constexpr int SLOTS = (WPS == 1) ? kThreads : 32;     // sample slots per block
+    constexpr int SLOTS = (WPS == 1) ? kThreads : 32;     // sample slots per virtual block
     constexpr int TS = SLOTS * ST;
     constexpr int NV = 2 * NB;
+    constexpr int NT = kThreads * VB;
 
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int C = p.C;                 // pulses per chunk (multiple of NB)
     const int CT = C * WPS;            // staged rows
-    float4* fwd4 = reinterpret_cast<float4*>(smem_raw);
+    constexpr int TIL = x2_tab_il(SC == SC_TABLE, BWD), TSEP = x2_tab_sep(SC == SC_TABLE, BWD);   // table entries staged
+    // layout: [{sin, cos} pairs @ 0][fwd rows][bwd rows][sin[] | cos[]][per virtual block: scratch, acc, xq].  The separate
+    // tables sit BEHIND the run-time sized rows on purpose: ptxas then addresses them as [R + UR + imm]; at a
+    // compile-time offset it materialises the base in a vector register and adds it per look-up (+4 % on the step)
+    const u64* tsc = reinterpret_cast<const u64*>(smem_raw);
+    float4* fwd4 = reinterpret_cast<float4*>(smem_raw + (size_t)TIL * 8);
     float4* bwd4 = fwd4 + CT;
-    float* acc = reinterpret_cast<float*>(bwd4 + (BWD ? CT : 0));
-    float* scratch = acc + (BWD ? (size_t)kWarps * C * 2 : 0);
-    constexpr int TLEN = (SC == SC_TABLE) ? (BWD ? UQOC_SINCOS_TABLE_LEN : kTabN) : 0;   // table entries staged
-    float* tsin = scratch + 32;
-    float* tcos = tsin + TLEN;
-    float* xq = tcos + TLEN;                                // [kWarps][ST][5][32], WPS > 1 only
+    float* tsin = reinterpret_cast<float*>(bwd4 + (BWD ? CT : 0));
+    float* tcos = tsin + TSEP;
+    float* vb_base = tcos + TSEP;
+    const int acc_len = BWD ? kWarps * C * 2 : 0;
+    const int xq_len = (WPS > 1) ? kWarps * ST * 5 * 32 : 0;
+    const int vb_len = 32 + acc_len + xq_len;
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int split = blockIdx.x % p.splits;
-    const int b = blockIdx.x / p.splits;
+#ifdef UQOC_FIN_TIMING
+    if (p.fin.ticket != nullptr && blockIdx.x == 0 && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(p.fin.ticket)[7] = t;
+    }
+#endif
+    const int vb = (VB == 1) ? 0 : tid / kThreads;         // virtual block
+    const int vt = (VB == 1) ? tid : tid % kThreads;       // thread inside it
+    const int lane = vt & 31;
+    const int warp = vt >> 5;
+    float* scratch = vb_base + (size_t)vb * vb_len;
+    float* acc = scratch + 32;
+    float* xq = acc + acc_len;                              // [kWarps][ST][5][32], WPS > 1 only
+
+    const int cblk = blockIdx.x % p.cps;                   // this block among the target's blocks
+    const int b = blockIdx.x / p.cps;
+    const int split = cblk * VB + vb;                      // sample-tile stream
     const int L = p.L;
     const int rb = (WPS == 1) ? 0 : warp * C;              // first staged row of this warp's chunk
-    const int slot = (WPS == 1) ? tid : lane;
+    const int slot = (WPS == 1) ? vt : lane;
     const bool lead = (WPS == 1) || warp == 0;             // the warp that reports per-sample outputs
 
     {
-        // sin/cos table: all 16 loads of a thread in flight before the pulse trigonometry, stored after it
-        // (a load -> store loop serialises 8 L2 round trips per thread: 4 us of a 55 us launch at BASELINE config 3)
-        float tv[2][(TLEN > 0 ? TLEN : kThreads) / kThreads];
-        if (SC == SC_TABLE) {
+        // sin/cos tables: all loads of a thread in flight before the pulse trigonometry, stored after it
+        // (a load -> store loop serialises the L2 round trips: 4 us of a 55 us launch at BASELINE config 3)
+        constexpr int TVI = (TIL * 2 / 4 + NT - 1) / NT, TVS = (TSEP / 4 + NT - 1) / NT;   // float4 per thread
+        float4 tvi[TVI > 0 ? TVI : 1], tvs[2][TVS > 0 ? TVS : 1];
 #pragma unroll
-            for (int u = 0; u < TLEN / kThreads; ++u) {
-                tv[0][u] = g_sin_table[tid + u * kThreads];
-                tv[1][u] = g_cos_table[tid + u * kThreads];
+        for (int u = 0; u < TVI; ++u) {
+            const int i = tid + u * NT;
+            if (i < TIL / 2) tvi[u] = reinterpret_cast<const float4*>(g_sincos_table)[i];
+        }
+#pragma unroll
+        for (int u = 0; u < TVS; ++u) {
+            const int i = tid + u * NT;
+            if (i < TSEP / 4) {
+                tvs[0][u] = reinterpret_cast<const float4*>(g_sin_table)[i];
+                tvs[1][u] = reinterpret_cast<const float4*>(g_cos_table)[i];
             }
         }
         const float* pb = p.pulses + (size_t)b * L * 2;
-        for (int i = tid; i < CT; i += kThreads) {
+        for (int i = tid; i < CT; i += NT) {
             const int ic = i < L ? i : L - 1;
             const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
             const double phi = (double)pb[2 * ic];
@@ -314,13 +377,19 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
             }
         }
         if (BWD) {
-            for (int i = tid; i < kWarps * C * 2; i += kThreads) acc[i] = 0.0f;
+            for (int i = vt; i < acc_len; i += kThreads) acc[i] = 0.0f;
         }
-        if (SC == SC_TABLE) {
 #pragma unroll
-            for (int u = 0; u < TLEN / kThreads; ++u) {
-                tsin[tid + u * kThreads] = tv[0][u];
-                tcos[tid + u * kThreads] = tv[1][u];
+        for (int u = 0; u < TVI; ++u) {
+            const int i = tid + u * NT;
+            if (i < TIL / 2) reinterpret_cast<float4*>(smem_raw)[i] = tvi[u];
+        }
+#pragma unroll
+        for (int u = 0; u < TVS; ++u) {
+            const int i = tid + u * NT;
+            if (i < TSEP / 4) {
+                reinterpret_cast<float4*>(tsin)[i] = tvs[0][u];
+                reinterpret_cast<float4*>(tcos)[i] = tvs[1][u];
             }
         }
     }
@@ -332,8 +401,11 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     float fsum = 0.0f;
 
     for (int tile = split; tile < p.n_tiles; tile += p.splits) {
-        // ---- per-sample constants, packed pairwise: pair u = samples (2u, 2u+1) of this thread
-        F2 ka[NP], ka2[NP], kr[NP], kr2[NP], kdl[NP], kae[NP];   // ka / ka2: table-index slopes when SC == SC_TABLE
+        // ---- per-sample constants; the table-index slopes ride two SAMPLES per register pair (pair u = samples 2u, 2u+1)
+        F2 ka[NP], ka2[NP];      // half / full angle per unit tau: table-index slopes (SC_TABLE) or radians
+        F2 kr[NP], kr2[NP], kdl[NP], kae[NP];   // two-samples-per-pair constants
+        F2 RD[ST];               // per sample (1/w, delta/w): (s', q3) = sin h * RD
+        float kdl_s[ST], kr_s[ST], kr2_s[ST], kae_s[ST];
         bool valid[ST];
         size_t sidx[ST];
         {
@@ -352,6 +424,11 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                     }
                 }
                 kc[u] = make_sample_const<float>(delta, eps);
+                RD[u] = f2(kc[u].r, kc[u].rd);
+                kdl_s[u] = kc[u].delta;
+                kr_s[u] = kc[u].r;
+                kr2_s[u] = kc[u].r2;
+                kae_s[u] = kc[u].ae;
             }
 #pragma unroll
             for (int u = 0; u < NP; ++u) {
@@ -370,11 +447,6 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
         }
 
         // ---------------- forward sweep over this warp's chunk ----------------
-        // The per-pulse scalars (sin/cos, q) are computed with two SAMPLES per register pair; the running product
-        // keeps two COMPONENTS of one sample per pair, X = (a, b), Y = (c, d), so that every Hamilton-product
-        // instruction is  acc += {X | Y with a free swap / sign modifier} * scalar: the per-sample scalar rides in
-        // the 32-bit broadcast slot and X / Y come from the operand-reuse cache -- one fresh 64-bit register read
-        // per FFMA2 instead of two (tools/ubench/fma_ubench.cu: 95 % vs 76 % of the pipe).
         F2 X[ST], Y[ST];
         int par[ST];
 #pragma unroll
@@ -385,38 +457,65 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
         }
 #pragma unroll kX2FwdUnroll
         for (int jj = 0; jj < C; ++jj) {
-            // per-pulse values are warp-uniform: f2b() lets ptxas use the 32-bit broadcast operand form (R.F32),
-            // which costs no 64-bit register-file read (tools/ubench/fma_ubench.cu modes 5/6)
             const float4 row = fwd4[rb + jj];
-            const F2 cc = f2b(row.x), ss = f2b(row.y), tau = f2b(row.z);
-            F2 h[NP], s[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP];
+            const F2 tau = f2b(row.z);
+            float cs_[ST], a1_[ST], a2_[ST], a3_[ST];      // per sample: cos h, q1, q2, q3 (32-bit broadcast operands)
             int kb[ST];
-            if constexpr (SC == SC_TABLE) {
-                sincos2_tab<NP, false>(tau, ka, s, c, kb, tsin, tcos);
-            } else {
+            if constexpr (kFwdForm == 0 || SC != SC_TABLE) {
+                // two samples per register pair (per-pulse values are warp-uniform: f2b() lets ptxas use the 32-bit
+                // broadcast operand form, which costs no 64-bit register-file read)
+                const F2 cc = f2b(row.x), ss = f2b(row.y);
+                F2 h[NP], sn[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP];
+                if constexpr (SC == SC_TABLE) {
+                    sincos2_tab_sep<NP, false>(tau, ka, sn, c, kb, tsin, tcos);
+                } else {
 #pragma unroll
-                for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
-                sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
+                    for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
+                    sincos2_n<NP, SC>(h, sn, c, kb);
+                }
+#pragma unroll
+                for (int u = 0; u < NP; ++u) sp[u] = mul2(sn[u], kr[u]);
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    q1[u] = mul2(sp[u], cc);
+                    q2[u] = mul2(sp[u], ss);
+                    q3[u] = mul2(sp[u], kdl[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    cs_[2 * u] = f2lo(c[u]);   cs_[2 * u + 1] = f2hi(c[u]);
+                    a1_[2 * u] = f2lo(q1[u]);  a1_[2 * u + 1] = f2hi(q1[u]);
+                    a2_[2 * u] = f2lo(q2[u]);  a2_[2 * u + 1] = f2hi(q2[u]);
+                    a3_[2 * u] = f2lo(q3[u]);  a3_[2 * u + 1] = f2hi(q3[u]);
+                }
+            } else {
+                // two components of one sample per pair after the table-index arithmetic: V = (sin h, cos h),
+                // (s', q3) = sin h (1/w, delta/w), (q1, q2) = s' (cos phi, sin phi)
+                const F2 CS = f2(row.x, row.y);
+                F2 V[ST], SQ[ST], Q12[ST];
+                sincos2_tab_il<NP, false>(tau, ka, V, kb, tsc);
+#pragma unroll
+                for (int v = 0; v < ST; ++v) SQ[v] = mul2(RD[v], f2b(f2lo(V[v])));
+#pragma unroll
+                for (int v = 0; v < ST; ++v) Q12[v] = mul2(CS, f2b(f2lo(SQ[v])));
+#pragma unroll
+                for (int v = 0; v < ST; ++v) {
+                    cs_[v] = f2hi(V[v]);
+                    a1_[v] = f2lo(Q12[v]);
+                    a2_[v] = f2hi(Q12[v]);
+                    a3_[v] = f2hi(SQ[v]);
+                }
             }
             if ((SC == SC_POLY || SC == SC_TABLE) && !BWD) {
 #pragma unroll
                 for (int u = 0; u < ST; ++u) par[u] ^= kb[u];
             }
-#pragma unroll
-            for (int u = 0; u < NP; ++u) sp[u] = mul2(s[u], kr[u]);
-#pragma unroll
-            for (int u = 0; u < NP; ++u) {
-                q1[u] = mul2(sp[u], cc);
-                q2[u] = mul2(sp[u], ss);
-                q3[u] = mul2(sp[u], kdl[u]);
-            }
+            // running product: two COMPONENTS of one sample per pair, X = (a, b), Y = (c, d); every instruction is
+            // acc += {X | Y with a free swap / sign modifier} * scalar (ptxas folds the modifiers only when the modified
+            // pair is the FIRST source operand)
 #pragma unroll
             for (int v = 0; v < ST; ++v) {
-                const int u = v >> 1;
-                const F2 cs = f2b((v & 1) ? f2hi(c[u]) : f2lo(c[u]));
-                const F2 a1 = f2b((v & 1) ? f2hi(q1[u]) : f2lo(q1[u]));
-                const F2 a2 = f2b((v & 1) ? f2hi(q2[u]) : f2lo(q2[u]));
-                const F2 a3 = f2b((v & 1) ? f2hi(q3[u]) : f2lo(q3[u]));
+                const F2 cs = f2b(cs_[v]), a1 = f2b(a1_[v]), a2 = f2b(a2_[v]), a3 = f2b(a3_[v]);
                 // (na, nb) = c (a, b) + q1 (-b, a) + q2 (-c, d) + q3 (-d, -c)
                 // (nc, nd) = c (c, d) + q1 (-d, c) + q2 (a, -b) + q3 (b, a)
                 F2 nX = mul2(X[v], cs);
@@ -446,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                 dst[0] = Pin[u].a; dst[32] = Pin[u].b; dst[64] = Pin[u].c; dst[96] = Pin[u].d;
                 dst[128] = __int_as_float(par[u] & 1);
             }
-            __syncthreads();
+            vb_sync<VB>(vb);
 #pragma unroll
             for (int u = 0; u < ST; ++u) {
                 const float* s0 = xq + ((size_t)u * 5) * 32 + lane;
@@ -464,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                 PL[u] = run;
                 par[u] = ptot;                             // parity of the whole train (U_out sign)
             }
-            __syncthreads();                               // xq is rewritten by the next tile
+            vb_sync<VB>(vb);                               // xq is rewritten by the next tile
         }
 
         // ---------------- fidelity epilogue (scalar, once per sample) ----------------
@@ -495,10 +594,9 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
 
         if constexpr (BWD) {
             // ---------------- adjoint seed at the end of this warp's chunk ----------------
-            F2 A[NP], Bq[NP], W3[NP];
+            float a_[ST], b_[ST], w_[ST];
             {
                 const float4 rowL = fwd4[rb + C - 1];      // (cos phi, sin phi) of the chunk's last pulse
-                float a_[ST], b_[ST], w_[ST];
 #pragma unroll
                 for (int u = 0; u < ST; ++u) {
                     float wgt = 0.0f;
@@ -517,27 +615,50 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                     b_[u] = Wq.c * rowL.x - Wq.b * rowL.y;
                     w_[u] = Wq.d;
                 }
+            }
+            // ---------------- backward sweep ----------------
+            if constexpr (kBwdForm <= 1 || SC != SC_TABLE) {
+                // two SAMPLES per register pair (A, Bq, W3 of samples 2u, 2u+1)
+                F2 A[NP], Bq[NP], W3[NP];
 #pragma unroll
                 for (int u = 0; u < NP; ++u) {
                     A[u] = f2(a_[2 * u], a_[2 * u + 1]);
                     Bq[u] = f2(b_[2 * u], b_[2 * u + 1]);
                     W3[u] = f2(w_[2 * u], w_[2 * u + 1]);
                 }
-            }
-            // ---------------- backward sweep ----------------
-            const F2 one = f2b(1.0f);
-            for (int jb = C / NB - 1; jb >= 0; --jb) {
-                float v[NV];
+                const F2 one = f2b(1.0f);
+                for (int jb = C / NB - 1; jb >= 0; --jb) {
+                    float v[NV];
 #pragma unroll
-                for (int e = NB - 1; e >= 0; --e) {
-                    const float4 row = bwd4[rb + jb * NB + e];
-                    const F2 cd = f2b(row.x), sd = f2b(row.y), tau = f2b(row.z);
-                    F2 gp = f2b(0.0f), gt = f2b(0.0f);
-                    F2 h[NP], s[NP], c[NP], s2[NP], C2[NP], Sr[NP], k1_[NP], t[NP], uu[NP], K[NP], BS[NP], A1[NP], B1[NP], Wz[NP];
-                    int kb[ST];
-                    if constexpr (SC == SC_TABLE) {
-                        // (sin 2h, cos 2h) straight from the full-period table
-                        sincos2_tab<NP, true>(tau, ka2, s2, C2, kb, tsin, tcos);
+                    for (int e = NB - 1; e >= 0; --e) {
+                        const float4 row = bwd4[rb + jb * NB + e];
+                        const F2 cd = f2b(row.x), sd = f2b(row.y), tau = f2b(row.z);
+                        F2 gp = f2b(0.0f), gt = f2b(0.0f);
+                        F2 s2[NP], C2[NP], Sr[NP], k1_[NP], t[NP], uu[NP], K[NP], BS[NP], A1[NP], B1[NP], Wz[NP];
+                        int kb[ST];
+                        if constexpr (SC == SC_TABLE && kBwdForm == 0) {
+                            // (sin 2h, cos 2h) straight from the full-period table
+                            sincos2_tab_sep<NP, true>(tau, ka2, s2, C2, kb, tsin, tcos);
+                        } else if constexpr (SC == SC_TABLE) {
+                            F2 V2[ST];                      // per sample on the interleaved pair, then re-paired
+                            sincos2_tab_il<NP, true>(tau, ka2, V2, kb, tsc);
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                s2[u] = f2(f2lo(V2[2 * u]), f2lo(V2[2 * u + 1]));
+                                C2[u] = f2(f2hi(V2[2 * u]), f2hi(V2[2 * u + 1]));
+                            }
+                        } else {
+                            F2 h[NP], s[NP], c[NP];
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
+                            sincos2_n<NP, SC>(h, s, c, kb);
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                const F2 sh = add2(s[u], s[u]);
+                                C2[u] = fma2(neg2(sh), s[u], one);   // cos 2h
+                                s2[u] = mul2(sh, c[u]);              // sin 2h
+                            }
+                        }
 #pragma unroll
                         for (int u = 0; u < NP; ++u) {
                             t[u] = fma2(kdl[u], W3[u], A[u]);
@@ -548,66 +669,117 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
                             Sr[u] = mul2(s2[u], kr[u]);
                             gt = fma2(kae[u], t[u], gt);
                         }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
-                        sincos2_n<NP, SC>(h, s, c, kb, tsin, tcos);
 #pragma unroll
                         for (int u = 0; u < NP; ++u) {
-                            s2[u] = add2(s[u], s[u]);
-                            t[u] = fma2(kdl[u], W3[u], A[u]);
-                            uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                            k1_[u] = fma2(neg2(C2[u]), kr2[u], kr2[u]);
+                            BS[u] = mul2(Bq[u], Sr[u]);
+                            B1[u] = mul2(Bq[u], C2[u]);
+                            gp = fma2(Sr[u], Bq[u], gp);
                         }
 #pragma unroll
                         for (int u = 0; u < NP; ++u) {
-                            C2[u] = fma2(neg2(s2[u]), s[u], one);
-                            Sr[u] = mul2(mul2(s2[u], kr[u]), c[u]);
-                            gt = fma2(kae[u], t[u], gt);
+                            K[u] = mul2(k1_[u], t[u]);
+                            gp = fma2(neg2(k1_[u]), uu[u], gp);
+                            B1[u] = fma2(neg2(uu[u]), Sr[u], B1[u]);
+                            Wz[u] = fma2(W3[u], C2[u], neg2(BS[u]));
                         }
-                    }
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        k1_[u] = fma2(neg2(C2[u]), kr2[u], kr2[u]);
-                        BS[u] = mul2(Bq[u], Sr[u]);
-                        B1[u] = mul2(Bq[u], C2[u]);
-                        gp = fma2(Sr[u], Bq[u], gp);
-                    }
+                        for (int u = 0; u < NP; ++u) {
+                            A1[u] = fma2(A[u], C2[u], K[u]);
+                            W3[u] = fma2(kdl[u], K[u], Wz[u]);
+                        }
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        K[u] = mul2(k1_[u], t[u]);
-                        gp = fma2(neg2(k1_[u]), uu[u], gp);
-                        B1[u] = fma2(neg2(uu[u]), Sr[u], B1[u]);
-                        Wz[u] = fma2(W3[u], C2[u], neg2(BS[u]));
-                    }
+                        for (int u = 0; u < NP; ++u) A1[u] = fma2(kdl[u], BS[u], A1[u]);
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        A1[u] = fma2(A[u], C2[u], K[u]);
-                        W3[u] = fma2(kdl[u], K[u], Wz[u]);
+                        for (int u = 0; u < NP; ++u) {
+                            A[u] = fma2(neg2(B1[u]), sd, mul2(A1[u], cd));
+                            Bq[u] = fma2(B1[u], cd, mul2(A1[u], sd));
+                        }
+                        v[2 * e] = f2lo(gp) + f2hi(gp);
+                        v[2 * e + 1] = f2lo(gt) + f2hi(gt);
                     }
+                    int base = 0;
+                    LaneReduce<float, NV, 1>::run(v, lane, base);
+                    constexpr int NF = reduce_final_count(NV, 1);
+                    constexpr int DUP = reduce_dup_mask(NV, 1);
+                    if ((lane & DUP) == 0) {
+                        // WPS = 1: per-warp slice of the whole train;  WPS = 4: this warp's chunk of the train
+                        float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
 #pragma unroll
-                    for (int u = 0; u < NP; ++u) A1[u] = fma2(kdl[u], BS[u], A1[u]);
-#pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        A[u] = fma2(neg2(B1[u]), sd, mul2(A1[u], cd));
-                        Bq[u] = fma2(B1[u], cd, mul2(A1[u], sd));
+                        for (int m = 0; m < NF; ++m) dst[m] += v[m];
                     }
-                    v[2 * e] = f2lo(gp) + f2hi(gp);
-                    v[2 * e + 1] = f2lo(gt) + f2hi(gt);
                 }
-                int base = 0;
-                LaneReduce<float, NV, 1>::run(v, lane, base);
-                constexpr int NF = reduce_final_count(NV, 1);
-                constexpr int DUP = reduce_dup_mask(NV, 1);
-                if ((lane & DUP) == 0) {
-                    // WPS = 1: per-warp slice of the whole train;  WPS = 4: this warp's chunk of the train
-                    float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
+            } else {
+                // per sample: Z = (A, W3) as one register pair, Bq as a scalar.
+                //   (t, -uu) = Z + (-delta)(-W3, A);  Sr = sin 2h / w, k1 = (1 - cos 2h)/w^2;
+                //   d/dtau += ae t,  d/dphi += Sr Bq + k1 (-uu);  Y = (k1 t, -Bq Sr);
+                //   Z <- cos 2h Z + Y + delta (-Y.hi, Y.lo),  B1 = Bq cos 2h + (-uu) Sr;  then the frame change by dphi.
+                F2 Z[ST];
+                float Bs[ST];
 #pragma unroll
-                    for (int m = 0; m < NF; ++m) dst[m] += v[m];
+                for (int u = 0; u < ST; ++u) {
+                    Z[u] = f2(a_[u], w_[u]);
+                    Bs[u] = b_[u];
+                }
+                for (int jb = C / NB - 1; jb >= 0; --jb) {
+                    float v[NV];
+#pragma unroll
+                    for (int e = NB - 1; e >= 0; --e) {
+                        const float4 row = bwd4[rb + jb * NB + e];
+                        const float cd = row.x, sd = row.y;
+                        const F2 tau = f2b(row.z);
+                        F2 V2[ST];                         // (sin 2h, cos 2h)
+                        int kb[ST];
+                        sincos2_tab_il<NP, true>(tau, ka2, V2, kb, tsc);
+                        float gp = 0.0f, gt = 0.0f;
+                        F2 T2[ST], Yk[ST], Z1[ST];
+                        float Sr[ST], k1[ST], B1[ST];
+#pragma unroll
+                        for (int u = 0; u < ST; ++u) T2[u] = fma2(swp2_np(Z[u]), f2b(-kdl_s[u]), Z[u]);      // (t, -uu)
+#pragma unroll
+                        for (int u = 0; u < ST; ++u) {
+                            Sr[u] = f2lo(V2[u]) * kr_s[u];
+                            k1[u] = fmaf(-f2hi(V2[u]), kr2_s[u], kr2_s[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < ST; ++u) {
+                            gt = fmaf(kae_s[u], f2lo(T2[u]), gt);
+                            gp = fmaf(Sr[u], Bs[u], gp);
+                            Yk[u] = f2(k1[u] * f2lo(T2[u]), -(Bs[u] * Sr[u]));
+                            B1[u] = Bs[u] * f2hi(V2[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < ST; ++u) {
+                            gp = fmaf(k1[u], f2hi(T2[u]), gp);
+                            B1[u] = fmaf(f2hi(T2[u]), Sr[u], B1[u]);
+                            Z1[u] = fma2(Z[u], f2b(f2hi(V2[u])), Yk[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < ST; ++u) Z1[u] = fma2(swp2_np(Yk[u]), f2b(kdl_s[u]), Z1[u]);
+#pragma unroll
+                        for (int u = 0; u < ST; ++u) {
+                            const float A1 = f2lo(Z1[u]);
+                            Bs[u] = fmaf(A1, sd, B1[u] * cd);
+                            Z[u] = f2(fmaf(-B1[u], sd, A1 * cd), f2hi(Z1[u]));
+                        }
+                        v[2 * e] = gp;
+                        v[2 * e + 1] = gt;
+                    }
+                    int base = 0;
+                    LaneReduce<float, NV, 1>::run(v, lane, base);
+                    constexpr int NF = reduce_final_count(NV, 1);
+                    constexpr int DUP = reduce_dup_mask(NV, 1);
+                    if ((lane & DUP) == 0) {
+                        float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
+#pragma unroll
+                        for (int m = 0; m < NF; ++m) dst[m] += v[m];
+                    }
                 }
             }
         }
     }
 
+    // ---------------- block epilogue: deterministic fixed-order reductions ----------------
     {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
@@ -617,22 +789,33 @@ __global__ void __launch_bounds__(kThreads, x2_min_blocks(NP, SC, WPS)) su2_kern
     if (tid == 0 && p.Fsum_part != nullptr) {
         float tot = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) tot += scratch[w];
-        p.Fsum_part[(size_t)split * p.B + b] = tot;
+        for (int q = 0; q < VB; ++q) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += vb_base[(size_t)q * vb_len + w];
+        }
+        p.Fsum_part[(size_t)cblk * p.B + b] = tot;
     }
     if constexpr (BWD) {
-        float* gout = p.G_part + ((size_t)split * p.B + b) * L * 2;
+        float* gout = p.G_part + ((size_t)cblk * p.B + b) * L * 2;
         const int LC2 = C * 2;
-        for (int i = tid; i < 2 * L; i += kThreads) {
-            float tot;
-            if constexpr (WPS == 1) {
-                tot = 0.0f;
+        for (int i = tid; i < 2 * L; i += NT) {
+            float tot = 0.0f;
 #pragma unroll
-                for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
-            } else {
-                tot = acc[i];                              // chunks are consecutive: flat index == pulse index
+            for (int q = 0; q < VB; ++q) {
+                const float* a_q = vb_base + (size_t)q * vb_len + 32;
+                if constexpr (WPS == 1) {
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) tot += a_q[(size_t)w * LC2 + i];
+                } else {
+                    tot += a_q[i];                         // chunks are consecutive: flat index == pulse index
+                }
             }
             gout[i] = (i & 1) ? tot : tot * 0.5f;
+        }
+        if (p.fin.ticket != nullptr) {
+            __syncthreads();                               // the accumulators are dead: the epilogue reuses shared memory
+            const FinParams<float> fin = p.fin;            // a copy: the kernel parameters themselves stay in the constant bank
+            su2_block_finalize<float>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw);
         }
     }
 }

@@ -38,13 +38,16 @@ class GraphedFusedStep:
         self.h_target = torch.zeros(B, 2, 2, dtype=cdt).pin_memory()
         self.h_err = torch.zeros(2, B * self.M, dtype=dtype).pin_memory() if explicit_error else None
         self.h_rng = torch.zeros(2, dtype=torch.int64).pin_memory()
-        self.h_out = torch.zeros(3 + B + B * L * 2, dtype=dtype).pin_memory()       # [loss, Fbar, dloss | Fsum | grad]
+        self.h_out = torch.zeros(B * L * 2 + B + 4, dtype=dtype).pin_memory()       # [grad | Fsum | loss, Fbar, dloss, -]
         self.d_pulses = torch.zeros(B, L, 2, dtype=dtype, device=self.dev)
         self.d_target = torch.zeros(B, 2, 2, dtype=cdt, device=self.dev)
         self.d_err = torch.zeros(2, B * self.M, dtype=dtype, device=self.dev) if explicit_error else None
         self.d_rng = torch.zeros(2, dtype=torch.int64, device=self.dev)
-        self.d_out = torch.zeros(3 + B + B * L * 2, dtype=dtype, device=self.dev)
+        self.d_out = torch.zeros(B * L * 2 + B + 4, dtype=dtype, device=self.dev)
         self.h_rng[0] = seed
+        self._flags = flags | FLAG_RNG_FROM_DEVICE | ops.FLAG_RAW_TARGET
+        # private workspace: the captured launch bakes its address in, so it must not be the shared grow-only one
+        self.ws = ops.su2_workspace(B, L, self.M, dtype, self._flags, self.dev)
         self._step = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._stream = torch.cuda.Stream(self.dev)
@@ -57,9 +60,10 @@ class GraphedFusedStep:
             self.d_err.copy_(self.h_err, non_blocking=True)
         self.d_rng.copy_(self.h_rng, non_blocking=True)
         tc = ops.raw_target(self.d_target, self.d_pulses.dtype)        # a view: the kernel forms the trace coefficients
-        Fsum, G = self.d_out[3:3 + B], self.d_out[3 + B:]
+        n_g = B * L * 2
+        G, Fsum, lo = self.d_out[:n_g], self.d_out[n_g:n_g + B], self.d_out[n_g + B:n_g + B + 3]
         ops._launch_fwdbwd_loss(self.d_pulses, tc, self.d_err, M, self.sigma, self.d_rng.data_ptr(), 0, self.loss, self.tau, self.k,
-                                None, None, Fsum, G, self.d_out[:3], self.flags | FLAG_RNG_FROM_DEVICE | ops.FLAG_RAW_TARGET)
+                                None, None, Fsum, G, lo, self._flags, ws=self.ws)
         self.h_out.copy_(self.d_out, non_blocking=True)
 
     def capture(self):
@@ -86,7 +90,9 @@ class GraphedFusedStep:
             self.h_err.copy_(error)
         self._step += 1
         self.h_rng[1] = self._step
-        self.graph.replay()
-        self._stream.synchronize()
+        with torch.cuda.stream(self._stream):        # CUDAGraph.replay() launches on the CURRENT stream
+            self.graph.replay()
+        self._stream.synchronize()                   # the D2H copy has landed: the returned views are valid
         B, L = self.B, self.L
-        return self.h_out[0], self.h_out[3 + B:].view(B, L, 2), self.h_out[3:3 + B] / self.M
+        n_g = B * L * 2
+        return self.h_out[n_g + B], self.h_out[:n_g].view(B, L, 2), self.h_out[n_g:n_g + B] / self.M

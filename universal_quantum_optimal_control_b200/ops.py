@@ -62,16 +62,48 @@ def _real_dtype(t: torch.Tensor) -> torch.dtype:
 _WORKSPACES: dict = {}
 
 
+def alloc_workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """A workspace buffer for the library: ZERO-filled (its first 256 bytes are the ticket counter of the in-kernel
+    epilogue, include/uqoc.h) and at least 1 MiB.  Owners of CUDA graphs allocate their own so that the address a
+    captured launch baked in stays alive and private."""
+    return torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+
+
 def _workspace(nbytes: int, device: torch.device) -> Optional[torch.Tensor]:
-    """Grow-only scratch buffer per (device, stream) -- the library never allocates."""
+    """Grow-only scratch buffer per (device, stream) -- the library never allocates.  Not for captured launches
+    (a later, larger request replaces the buffer): graph owners pass their own ``ws``."""
     if nbytes <= 0:
         return None
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        buf = alloc_workspace(nbytes, device)
         _WORKSPACES[key] = buf
     return buf
+
+
+class _on_device:
+    """``cudaSetDevice`` is the caller's job (include/uqoc.h): make the tensors' device current around a library
+    call when it is not already (the library takes the SM count and launches on the CURRENT device)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device: torch.device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _call(name: str, device: torch.device, *args) -> None:
+    with _on_device(device):
+        check(getattr(_lib.lib(), name)(*args), name)
 
 
 def tuning_flags(st: int = 0, lps: int = 0, splits: int = 0, fast_sincos: bool = False, no_packed: bool = False,
@@ -148,8 +180,7 @@ def target_coeffs(U_target: torch.Tensor, real_dtype: torch.dtype) -> torch.Tens
         U_target = U_target.to(torch.complex64 if real_dtype == torch.float32 else torch.complex128)
     ur = torch.view_as_real(U_target.resolve_conj()).to(real_dtype).contiguous()
     out = torch.empty(U_target.shape[0], 8, dtype=real_dtype, device=U_target.device)
-    check(_lib.lib().uqoc_su2_target_coeffs(_ptr(ur), U_target.shape[0], _ptr(out), _dt(out), _stream(out.device)),
-          "uqoc_su2_target_coeffs")
+    _call("uqoc_su2_target_coeffs", out.device, _ptr(ur), U_target.shape[0], _ptr(out), _dt(out), _stream(out.device))
     return out
 
 
@@ -157,8 +188,8 @@ def philox_errors(B: int, M: int, sigma: Sequence[float] = (1.0, 0.05), seed: in
                   device="cuda", dtype=torch.float32) -> torch.Tensor:
     """(2, B*M) errors from the library's counter-based stream (``uqoc_philox_errors``)."""
     out = torch.empty(2, B * M, dtype=dtype, device=device)
-    check(_lib.lib().uqoc_philox_errors(B, M, j0, float(sigma[0]), float(sigma[1]), seed, offset, _ptr(out), _dt(out),
-                                        _stream(out.device)), "uqoc_philox_errors")
+    _call("uqoc_philox_errors", out.device, B, M, j0, float(sigma[0]), float(sigma[1]), seed, offset, _ptr(out), _dt(out),
+                                        _stream(out.device))
     return out
 
 
@@ -170,100 +201,125 @@ def fp32_peak_tflops(iters: int = 4096, mode: int = F32) -> Tuple[float, float]:
 
 
 # ----------------------------------------------------------------------------- fused op
-def _launch_fwdbwd(pulses, tc, error, weight, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags):
+_WS_BYTES: dict = {}
+
+
+def _su2_ws_bytes(B, L, M, dt, flags, device) -> int:
+    """uqoc_su2_workspace_bytes, memoised per device (the plan depends on the SM count only)."""
+    key = (B, L, M, dt, flags, device.index)
+    n = _WS_BYTES.get(key)
+    if n is None:
+        with _on_device(device):
+            n = _WS_BYTES[key] = int(_lib.lib().uqoc_su2_workspace_bytes(B, L, M, dt, flags))
+    return n
+
+
+def su2_workspace(B: int, L: int, M: int, dtype: torch.dtype, flags: int, device) -> torch.Tensor:
+    """A private, zero-initialised workspace for one (B, L, M) launch shape (CUDA-graph owners)."""
+    dev = torch.device(device)
+    return alloc_workspace(_su2_ws_bytes(B, L, M, F64 if dtype == torch.float64 else F32, flags, dev), dev)
+
+
+def _ws_for(pulses, M, flags, ws):
     B, L, _ = pulses.shape
-    lib = _lib.lib()
-    dt = _dt(pulses)
-    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
-    ws = _workspace(ws_bytes, pulses.device)
-    check(lib.uqoc_su2_fwdbwd(_ptr(pulses), _ptr(tc), _ptr(error), _ptr(weight), B, L, M, j0, float(sigma[0]),
-                              float(sigma[1]), seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws),
-                              ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su2_fwdbwd")
+    n = _su2_ws_bytes(B, L, M, _dt(pulses), flags, pulses.device)
+    if ws is None:
+        ws = _workspace(n, pulses.device)
+    elif ws.numel() < n:
+        raise ValueError(f"workspace of {ws.numel()} bytes is too small for this launch shape ({n} bytes)")
+    return ws, n
 
 
-def _launch_fwdbwd_peer(pulses, tc, error, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, px):
-    """This rank's shard + fused [partials reduction | NVLink peer exchange]: Fsum / G come back summed over ranks."""
+def _launch_fwdbwd(pulses, tc, error, weight, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, ws=None):
+    B, L, _ = pulses.shape
+    ws, ws_bytes = _ws_for(pulses, M, flags, ws)
+    _call("uqoc_su2_fwdbwd", pulses.device, _ptr(pulses), _ptr(tc), _ptr(error), _ptr(weight), B, L, M, j0, sigma[0], sigma[1],
+          seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes, _dt(pulses), flags,
+          _stream(pulses.device))
+
+
+def _check_px(px, pulses):
     B, L, P = pulses.shape
     if not px.matches(B, L, P, pulses.dtype):
         raise ValueError(f"PeerExchange was built for (B, L, P, dtype) = {(px.B, px.L, px.P, px.dtype)}, "
                          f"got {(B, L, P, pulses.dtype)}")
-    lib = _lib.lib()
-    dt = _dt(pulses)
-    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
-    ws = _workspace(ws_bytes, pulses.device)
-    check(lib.uqoc_su2_fwdbwd_peer(_ptr(pulses), _ptr(tc), _ptr(error), None, B, L, M, j0, float(sigma[0]), float(sigma[1]),
-                                   seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes,
-                                   px.rank, px.world, px.data_ptrs, px.flag_ptrs, px.next_epoch(), dt, flags,
-                                   _stream(pulses.device)), "uqoc_su2_fwdbwd_peer")
 
 
-_WS_BYTES: dict = {}
-
-
-def _su2_ws_bytes(lib, B, L, M, dt, flags) -> int:
-    """uqoc_su2_workspace_bytes, memoised per device (the plan depends on the SM count only)."""
-    key = (B, L, M, dt, flags, torch.cuda.current_device())
-    n = _WS_BYTES.get(key)
-    if n is None:
-        n = _WS_BYTES[key] = int(lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags))
-    return n
-
-
-def _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags):
-    """Single-GPU step: fused kernel + (fused) partials reduction + loss epilogue, <= 2 launches."""
+def _launch_fwdbwd_peer(pulses, tc, error, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, px, ws=None):
+    """This rank's shard + fused [partials reduction | NVLink peer exchange]: Fsum / G come back summed over ranks."""
     B, L, _ = pulses.shape
-    lib = _lib.lib()
-    dt = _dt(pulses)
-    ws_bytes = _su2_ws_bytes(lib, B, L, M, dt, flags)
-    ws = _workspace(ws_bytes, pulses.device)
-    check(lib.uqoc_su2_fwdbwd_loss(_ptr(pulses), _ptr(tc), _ptr(error), B, L, M, float(sigma[0]), float(sigma[1]), seed, offset,
-                                   LOSS_KINDS[loss], float(tau), float(k), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G),
-                                   _ptr(loss_out), _ptr(ws), ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su2_fwdbwd_loss")
+    _check_px(px, pulses)
+    ws, ws_bytes = _ws_for(pulses, M, flags, ws)
+    _call("uqoc_su2_fwdbwd_peer", pulses.device, _ptr(pulses), _ptr(tc), _ptr(error), None, B, L, M, j0, sigma[0], sigma[1],
+          seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes, px.rank, px.world,
+          px.data_ptrs, px.flag_ptrs, px.next_epoch(), _dt(pulses), flags, _stream(pulses.device))
 
 
-def _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, U_out, F_out, err_out, Fsum, flags):
+def _launch_fwdbwd_peer_loss(pulses, tc, error, M, j0, M_total, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G,
+                             loss_out, flags, px, ws=None):
+    """Multi-GPU step in one call: shard + partials reduction + NVLink peer exchange + loss epilogue (one launch for
+    small exchange vectors)."""
     B, L, _ = pulses.shape
-    lib = _lib.lib()
-    dt = _dt(pulses)
-    ws_bytes = lib.uqoc_su2_workspace_bytes(B, L, M, dt, flags)
-    ws = _workspace(ws_bytes, pulses.device)
-    check(lib.uqoc_su2_forward(_ptr(pulses), _ptr(tc), _ptr(error), B, L, M, j0, float(sigma[0]), float(sigma[1]), seed,
-                               offset, _ptr(U_out), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(ws), ws_bytes, dt, flags,
-                               _stream(pulses.device)), "uqoc_su2_forward")
+    _check_px(px, pulses)
+    ws, ws_bytes = _ws_for(pulses, M, flags, ws)
+    _call("uqoc_su2_fwdbwd_peer_loss", pulses.device, _ptr(pulses), _ptr(tc), _ptr(error), B, L, M, j0, M_total, sigma[0],
+          sigma[1], seed, offset, LOSS_KINDS[loss], tau, k, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(loss_out),
+          _ptr(ws), ws_bytes, px.rank, px.world, px.data_ptrs, px.flag_ptrs, px.next_epoch(), _dt(pulses), flags,
+          _stream(pulses.device))
+
+
+def _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags,
+                        ws=None):
+    """Single-GPU step: fused kernel with the partials reduction + loss epilogue in its last block (one launch) or, for
+    large partial volumes, one or two follow-up launches."""
+    B, L, _ = pulses.shape
+    ws, ws_bytes = _ws_for(pulses, M, flags, ws)
+    _call("uqoc_su2_fwdbwd_loss", pulses.device, _ptr(pulses), _ptr(tc), _ptr(error), B, L, M, sigma[0], sigma[1], seed, offset,
+          LOSS_KINDS[loss], tau, k, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(loss_out), _ptr(ws), ws_bytes,
+          _dt(pulses), flags, _stream(pulses.device))
+
+
+def _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, U_out, F_out, err_out, Fsum, flags, ws=None):
+    B, L, _ = pulses.shape
+    ws, ws_bytes = _ws_for(pulses, M, flags, ws)
+    _call("uqoc_su2_forward", pulses.device, _ptr(pulses), _ptr(tc), _ptr(error), B, L, M, j0, sigma[0], sigma[1], seed,
+          offset, _ptr(U_out), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(ws), ws_bytes, _dt(pulses), flags,
+          _stream(pulses.device))
 
 
 def _finalize(Fsum, n_total, loss, tau, k, G):
     loss_out = torch.empty(3, dtype=Fsum.dtype, device=Fsum.device)
-    check(_lib.lib().uqoc_loss_finalize(_ptr(Fsum), Fsum.numel(), float(n_total), LOSS_KINDS[loss], float(tau), float(k),
-                                        _ptr(G), 0 if G is None else G.numel(), _ptr(loss_out), _dt(Fsum),
-                                        _stream(Fsum.device)), "uqoc_loss_finalize")
+    _call("uqoc_loss_finalize", Fsum.device, _ptr(Fsum), Fsum.numel(), float(n_total), LOSS_KINDS[loss], float(tau), float(k),
+          _ptr(G), 0 if G is None else G.numel(), _ptr(loss_out), _dt(Fsum), _stream(Fsum.device))
     return loss_out
 
 
 class _FusedPropagateLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pulses, tc, error, M, j0, M_total, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out):
+    def forward(ctx, pulses, tc, error, M, j0, M_total, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out, ws=None):
         B, L, _ = pulses.shape
         need_grad = ctx.needs_input_grad[0]
-        buf = torch.empty(B + (B * L * 2 if need_grad else 0), dtype=pulses.dtype, device=pulses.device)
-        Fsum, G = buf[:B], (buf[B:] if need_grad else None)
+        n_g = B * L * 2 if need_grad else 0          # one buffer [G | Fsum]: ONE exchange, G 16-byte aligned for any B
+        buf = torch.empty(n_g + B, dtype=pulses.dtype, device=pulses.device)
+        G, Fsum = (buf[:n_g] if need_grad else None), buf[n_g:]
         if need_grad and group is None:
             loss_out = torch.empty(3, dtype=pulses.dtype, device=pulses.device)
-            _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags)
+            _launch_fwdbwd_loss(pulses, tc, error, M, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum, G, loss_out, flags, ws)
         elif need_grad and isinstance(group, PeerExchange):
-            # exchange fused into the partials reduction over NVLink peer memory (no NCCL call): peer.py
-            _launch_fwdbwd_peer(pulses, tc, error, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, group)
-            loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
+            # exchange (NVLink peer memory, no NCCL call) and loss epilogue inside the fused kernel's last block: peer.py
+            loss_out = torch.empty(3, dtype=pulses.dtype, device=pulses.device)
+            _launch_fwdbwd_peer_loss(pulses, tc, error, M, j0, M_total, sigma, seed, offset, loss, tau, k, F_out, err_out, Fsum,
+                                     G, loss_out, flags, group, ws)
         else:
             if isinstance(group, PeerExchange):
                 group = group.group
             if need_grad:
-                _launch_fwdbwd(pulses, tc, error, None, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags)
+                _launch_fwdbwd(pulses, tc, error, None, M, j0, sigma, seed, offset, F_out, err_out, Fsum, G, flags, ws)
             else:
-                _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, None, F_out, err_out, Fsum, flags)
+                _launch_forward(pulses, tc, error, M, j0, sigma, seed, offset, None, F_out, err_out, Fsum, flags, ws)
             if group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)   # [Fsum | G]: the one exchange step
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)   # [G | Fsum]: the one exchange step
             loss_out = _finalize(Fsum, B * M_total, loss, tau, k, G)
         mean_fid = Fsum / M_total
         if need_grad:
@@ -274,14 +330,15 @@ class _FusedPropagateLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_mean):
         (G,) = ctx.saved_tensors
-        return (g_loss * G,) + (None,) * 15
+        return (g_loss * G,) + (None,) * 16
 
 
 def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error: Optional[torch.Tensor] = None,
                          monte_carlo: int, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, offset: int = 0,
                          loss: str = "sharp", tau: float = 0.99, k: float = 100, dtype: Optional[torch.dtype] = None,
                          fast_sincos: bool = False, flags: int = 0, group=None,
-                         F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None):
+                         F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None,
+                         workspace: Optional[torch.Tensor] = None):
     """Disorder-averaged loss of ``trainer.py:80-88`` and (through autograd) its pulse gradient.
 
     pulses (B, L, 2) real [phi, tau] (un-repeated); U_target (B, 2, 2) complex;
@@ -290,7 +347,8 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     torch.distributed process group) every rank handles samples
     j in [rank*M/R, (rank+1)*M/R) of every target and one all-reduce combines [Fsum | G]; with
     ``group`` a :class:`PeerExchange` that exchange is fused into the partials reduction over NVLink
-    peer memory (small exchange vectors: few targets).
+    peer memory (small exchange vectors: few targets).  ``workspace``: a private buffer from :func:`su2_workspace`
+    for callers that capture the launch in a CUDA graph (default: a shared grow-only buffer per stream).
     Returns ``(loss scalar, mean fidelity per target (B,))``.
     """
     if pulses.ndim != 3 or pulses.shape[-1] != 2:
@@ -320,7 +378,7 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
         error = shard_errors(error.to(rdt), B, M_total, j0, M).contiguous()
     fl = flags | (FLAG_FAST_SINCOS if fast_sincos else 0)
     return _FusedPropagateLoss.apply(p, tc, error, M, j0, M_total, tuple(float(s) for s in sigma), int(seed), int(offset),
-                                     loss, tau, k, fl, group, F_out, err_out)
+                                     loss, tau, k, fl, group, F_out, err_out, workspace)
 
 
 class _PropagateFidelity(torch.autograd.Function):
@@ -372,8 +430,8 @@ class _Generator(torch.autograd.Function):
     def forward(ctx, pulses, error):
         Bm, L, _ = pulses.shape
         U = torch.empty(Bm, 2, 2, 2, dtype=pulses.dtype, device=pulses.device)
-        check(_lib.lib().uqoc_su2_generator_forward(_ptr(pulses), _ptr(error), Bm, L, _ptr(U), _dt(pulses), 0,
-                                                    _stream(pulses.device)), "uqoc_su2_generator_forward")
+        _call("uqoc_su2_generator_forward", pulses.device, _ptr(pulses), _ptr(error), Bm, L, _ptr(U), _dt(pulses), 0,
+                                                    _stream(pulses.device))
         ctx.save_for_backward(pulses, error)
         return torch.view_as_complex(U)
 
@@ -383,8 +441,8 @@ class _Generator(torch.autograd.Function):
         Bm, L, _ = pulses.shape
         g = torch.view_as_real(gU.resolve_conj()).to(pulses.dtype).contiguous()
         gp = torch.empty_like(pulses)
-        check(_lib.lib().uqoc_su2_generator_backward(_ptr(pulses), _ptr(error), _ptr(g), Bm, L, _ptr(gp), _dt(pulses), 0,
-                                                     _stream(pulses.device)), "uqoc_su2_generator_backward")
+        _call("uqoc_su2_generator_backward", pulses.device, _ptr(pulses), _ptr(error), _ptr(g), Bm, L, _ptr(gp), _dt(pulses), 0,
+                                                     _stream(pulses.device))
         return gp, None
 
 
@@ -419,8 +477,7 @@ class _Fidelity(torch.autograd.Function):
     def forward(ctx, U, T, d, t_stride):
         Bm = U.shape[0]
         F = torch.empty(Bm, dtype=U.dtype, device=U.device)
-        check(_lib.lib().uqoc_fidelity_forward(_ptr(U), _ptr(T), Bm, d, t_stride, _ptr(F), _dt(U), _stream(U.device)),
-              "uqoc_fidelity_forward")
+        _call("uqoc_fidelity_forward", U.device, _ptr(U), _ptr(T), Bm, d, t_stride, _ptr(F), _dt(U), _stream(U.device))
         ctx.save_for_backward(U, T)
         ctx.args = (d, t_stride)
         return F
@@ -430,8 +487,8 @@ class _Fidelity(torch.autograd.Function):
         U, T = ctx.saved_tensors
         d, t_stride = ctx.args
         gU = torch.empty_like(U)
-        check(_lib.lib().uqoc_fidelity_backward(_ptr(U), _ptr(T), _ptr(gF.to(U.dtype).contiguous()), U.shape[0], d, t_stride,
-                                                _ptr(gU), _dt(U), _stream(U.device)), "uqoc_fidelity_backward")
+        _call("uqoc_fidelity_backward", U.device, _ptr(U), _ptr(T), _ptr(gF.to(U.dtype).contiguous()), U.shape[0], d, t_stride,
+                                                _ptr(gU), _dt(U), _stream(U.device))
         return gU, None, None, None
 
 
@@ -463,7 +520,7 @@ class _MeanLoss(torch.autograd.Function):
         n = F.numel()
         S = torch.empty(1, dtype=F.dtype, device=F.device)
         ws = _workspace(1024 * 8, F.device)
-        check(_lib.lib().uqoc_sum(_ptr(F), n, _ptr(S), _ptr(ws), ws.numel(), _dt(F), _stream(F.device)), "uqoc_sum")
+        _call("uqoc_sum", F.device, _ptr(F), n, _ptr(S), _ptr(ws), ws.numel(), _dt(F), _stream(F.device))
         out = _finalize(S, n, kind, tau, k, None)
         ctx.save_for_backward(out)
         ctx.shape = F.shape
@@ -542,20 +599,22 @@ def _su4_target(U_target: torch.Tensor, rdt: torch.dtype, B: int) -> torch.Tenso
     return torch.view_as_real(U_target.to(cdt).resolve_conj().contiguous()).contiguous()
 
 
-def _su4_launch(bwd, pulses, tgt, error, weight, M, j0, J, sigma, seed, offset, U_out, F_out, err_out, Fsum, G, flags):
+def _su4_launch(bwd, pulses, tgt, error, weight, M, j0, J, sigma, seed, offset, U_out, F_out, err_out, Fsum, G, flags, ws=None):
     B, L, _ = pulses.shape
-    lib = _lib.lib()
     dt = _dt(pulses)
-    ws_bytes = lib.uqoc_su4_workspace_bytes(B, L, M, dt, flags)
-    ws = _workspace(ws_bytes, pulses.device)
+    dev = pulses.device
+    with _on_device(dev):
+        ws_bytes = int(_lib.lib().uqoc_su4_workspace_bytes(B, L, M, dt, flags))
+    if ws is None:
+        ws = _workspace(ws_bytes, dev)
     if bwd:
-        check(lib.uqoc_su4_fwdbwd(_ptr(pulses), _ptr(tgt), _ptr(error), _ptr(weight), B, L, M, j0, float(J), float(sigma[0]),
-                                  float(sigma[1]), seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws),
-                                  ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su4_fwdbwd")
+        _call("uqoc_su4_fwdbwd", dev, _ptr(pulses), _ptr(tgt), _ptr(error), _ptr(weight), B, L, M, j0, float(J), float(sigma[0]),
+              float(sigma[1]), seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes, dt, flags,
+              _stream(dev))
     else:
-        check(lib.uqoc_su4_forward(_ptr(pulses), _ptr(tgt), _ptr(error), B, L, M, j0, float(J), float(sigma[0]),
-                                   float(sigma[1]), seed, offset, _ptr(U_out), _ptr(F_out), _ptr(err_out), _ptr(Fsum),
-                                   _ptr(ws), ws_bytes, dt, flags, _stream(pulses.device)), "uqoc_su4_forward")
+        _call("uqoc_su4_forward", dev, _ptr(pulses), _ptr(tgt), _ptr(error), B, L, M, j0, float(J), float(sigma[0]),
+              float(sigma[1]), seed, offset, _ptr(U_out), _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(ws), ws_bytes, dt, flags,
+              _stream(dev))
 
 
 class _FusedPropagateLossSU4(torch.autograd.Function):
@@ -563,8 +622,9 @@ class _FusedPropagateLossSU4(torch.autograd.Function):
     def forward(ctx, pulses, tgt, error, M, j0, M_total, J, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out):
         B, L, _ = pulses.shape
         need_grad = ctx.needs_input_grad[0]
-        buf = torch.empty(B + (B * L * 3 if need_grad else 0), dtype=pulses.dtype, device=pulses.device)
-        Fsum, G = buf[:B], (buf[B:] if need_grad else None)
+        n_g = B * L * 3 if need_grad else 0
+        buf = torch.empty(n_g + B, dtype=pulses.dtype, device=pulses.device)
+        G, Fsum = (buf[:n_g] if need_grad else None), buf[n_g:]
         _su4_launch(need_grad, pulses, tgt, error, None, M, j0, J, sigma, seed, offset, None, F_out, err_out, Fsum, G, flags)
         if group is not None:
             import torch.distributed as dist

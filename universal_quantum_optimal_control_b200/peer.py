@@ -27,10 +27,24 @@ MAX_WORLD = 16
 MAX_N = 1 << 18
 
 
+def _symmetric_memory():
+    """``torch.distributed._symmetric_memory`` is a private module (torch >= 2.5, interface as of 2.11): fail with a
+    clear message - callers fall back to the NCCL all-reduce - when it is absent or has changed shape."""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+    except ImportError as e:                     # pragma: no cover - depends on the torch build
+        raise RuntimeError(f"torch {torch.__version__} has no torch.distributed._symmetric_memory: {e}") from e
+    missing = [n for n in ("empty", "rendezvous") if not hasattr(symm_mem, n)]
+    if missing:                                  # pragma: no cover
+        raise RuntimeError(f"torch {torch.__version__}: torch.distributed._symmetric_memory lacks {missing}; "
+                           "PeerExchange needs empty() and rendezvous() -> handle.buffer_ptrs")
+    return symm_mem
+
+
 class PeerExchange:
     def __init__(self, group, B: int, L: int, P: int = 2, dtype: torch.dtype = torch.float32, device=None):
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
+        symm_mem = _symmetric_memory()
 
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -57,7 +71,9 @@ class PeerExchange:
         self.epoch = 0
 
     def next_epoch(self) -> int:
-        self.epoch = self.epoch + 1 if self.epoch < 0x7FFFFFF0 else 1
+        # a free-running uint32 (0 skipped: the flags start at 0): the kernels compare flags and epoch by their SIGNED
+        # difference, which stays valid across the wrap as long as the ranks are within 2^31 calls of each other
+        self.epoch = ((self.epoch + 1) & 0xFFFFFFFF) or 1
         return self.epoch
 
     def matches(self, B: int, L: int, P: int, dtype: torch.dtype) -> bool:

@@ -211,6 +211,7 @@ class GraphedTrainStep:
         self.s_loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.s_fid = torch.zeros(B, dtype=torch.float32, device=self.device)
         self._graphs = {}
+        self._ws = None                                               # private workspace (its address is captured)
         self._stream = torch.cuda.Stream(self.device)
 
     def _step_body(self, sigma):
@@ -221,7 +222,10 @@ class GraphedTrainStep:
                   flags=self.flags | 8)                               # 8 = UQOC_FLAG_RNG_FROM_DEVICE
         if pulses.shape[-1] == 3:
             raise NotImplementedError("device-resident Philox state is wired for the SU(2) kernels only")
-        loss, fid = fn(pulses, self.s_target, **kw)
+        if self._ws is None:                                          # first warm-up step, outside capture
+            self._ws = ops.su2_workspace(pulses.shape[0], pulses.shape[1], self.M, self.dtype or torch.float32,
+                                         kw["flags"] | ops.FLAG_RAW_TARGET, self.device)
+        loss, fid = fn(pulses, self.s_target, workspace=self._ws, **kw)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
         self.optimizer.step()
