@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--fast-sincos", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="tuning flags (tuning_flags())")
+    ap.add_argument("--chunks", type=int, default=4,
+                    help="N>1, large exchange vector: target chunks of the pipelined step (all-reduce of chunk n under kernel n+1)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="N>1: all-reduce of [Fsum|G] through NCCL, or fused into the partials reduction over NVLink peer "
                          "memory (uqoc_su2_fwdbwd_peer); auto = peer when the vector is small (<= 2^18 reals)")
@@ -266,27 +268,41 @@ def main():
     if wl["explicit"]:
         # this rank's shard of the (2, B*M_total) error tensor, generated once on the device
         err_d = uq.philox_errors(B, M, wl["sigma"], seed=1234, offset=0, j0=rank * M, device=dev, dtype=rdt)
-    buf = torch.empty(B * L * 2 + B, dtype=rdt, device=dev)      # [G | Fsum]: one exchange, G 16-byte aligned
-    G, Fsum = buf[:B * L * 2], buf[B * L * 2:]
+    n_g = B * L * 2
+    buf = torch.empty(n_g + B, dtype=rdt, device=dev)      # [G | Fsum]: one exchange, G 16-byte aligned
+    G, Fsum = buf[:n_g], buf[n_g:]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
-    # N>1 exchange step: NCCL all-reduce, or fused into the partials reduction over NVLink peer memory
-    px = None
+    # N>1 exchange step.  Small vectors (few targets): fused into the step over NVLink peer memory
+    # (uqoc_su2_fwdbwd_peer_loss).  MB-sized vectors: NCCL all-reduce per TARGET CHUNK, overlapped with the next chunk's
+    # kernel (PipelinedStep).
+    px, pipe = None, None
     if group is not None and args.exchange != "nccl":
         from universal_quantum_optimal_control_b200 import peer as peer_mod
-        if args.exchange == "peer" or (B + B * L * 2) <= peer_mod.MAX_N:
+        if args.exchange == "peer" or (B + n_g) <= peer_mod.MAX_N:
             px = uq.PeerExchange(group, B, L, 2, rdt, dev)
-
+    if px is None and err_d is None and (group is not None or args.chunks > 1):
+        pipe = uq.PipelinedStep(B, L, M_total, chunks=max(1, args.chunks), dtype=rdt, sigma=wl["sigma"], seed=1234, group=group,
+                                device=dev, flags=flags)
     loss_dev = torch.empty(3, dtype=rdt, device=dev)
+    launches = {"n": 0}
 
     def step_device(i):
-        if group is None:      # single GPU: fused kernel + (fused) partials reduction / loss epilogue, 2 launches
-            ops._launch_fwdbwd_loss(pulses_d, tc, err_d, M, wl["sigma"], 1234, i, "sharp", 0.99, 100, None, None, Fsum, G, loss_dev, flags)
+        """One step with device-resident inputs; counts the kernels of THIS library it launches."""
+        if px is not None:         # multi-GPU, small vector: one call, exchange + loss inside it
+            ops._launch_fwdbwd_peer_loss(pulses_d, tc, err_d, M, rank * M, M_total, wl["sigma"], 1234, i, "sharp", 0.99, 100, None, None,
+                                         Fsum, G, loss_dev, flags, px)
+            launches["n"] += 3     # fused kernel + reduction/exchange + loss epilogue (1 when the epilogue runs in-kernel)
             return loss_dev
-        if px is not None:
-            ops._launch_fwdbwd_peer(pulses_d, tc, err_d, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags, px)
-        else:
-            ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags)
-            dist.all_reduce(buf, group=group)
+        if pipe is not None:       # target chunks on two streams, all-reduce of chunk n under the kernel of chunk n+1
+            launches["n"] += len(pipe.bounds) + 1
+            return pipe.run_device(pulses_d, target_d, offset=i)
+        if group is None:          # single GPU: ONE library call (fused kernel + dependent-launched epilogue)
+            ops._launch_fwdbwd_loss(pulses_d, tc, err_d, M, wl["sigma"], 1234, i, "sharp", 0.99, 100, None, None, Fsum, G, loss_dev, flags)
+            launches["n"] += 2
+            return loss_dev
+        ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, i, None, None, Fsum, G, flags)
+        dist.all_reduce(buf, group=group)
+        launches["n"] += 3
         return ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
 
     def barrier():
@@ -299,40 +315,33 @@ def main():
         step_device(i)
     barrier()
 
-    # ---- timed region: K steps, each bracketed by events; L2 flushed between steps
+    # ---- timed region: K steps, each bracketed by events on the launching stream; L2 flushed between steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    launches["n"] = 0
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
         ev[i][0].record()
-        kev[i][0].record()
-        if px is not None:
-            ops._launch_fwdbwd_peer(pulses_d, tc, err_d, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags, px)
-            kev[i][1].record()                     # fused kernel + fused reduction/exchange kernel
-        else:
-            ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags)
-            kev[i][1].record()
-            if group is not None:
-                dist.all_reduce(buf, group=group)
-        loss_out = ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
+        loss_out = step_device(args.warmup + i)
         ev[i][1].record()
-    if group is None:
-        # single GPU: the step is ONE library call (fused kernel + fused reduction/loss epilogue); time it as such
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
-            ev[i][0].record()
-            loss_out = step_device(args.warmup + i)
-            ev[i][1].record()
     barrier()
+    n_launches = launches["n"]
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     loss_val = float(loss_out[0].item())
+
+    # ---- the dominant kernel alone (roofline): this rank's un-chunked fused launch, no exchange, same events / flush
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        kev[i][0].record()
+        ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, rank * M, wl["sigma"], 1234, args.warmup + i, None, None, Fsum, G, flags)
+        kev[i][1].record()
+    barrier()
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
 
     # ---- end-to-end: public API, host buffers, H2D + D2H inside the timed region
     grad_h = torch.empty(B, L, 2, dtype=rdt).pin_memory()
@@ -356,35 +365,47 @@ def main():
         loss_h.copy_(val.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    for i in range(args.warmup):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps      # host wall clock: host-side work counts end to end
+    def wall(fn):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            fn(args.warmup + i)
+        barrier()
+        return (time.perf_counter() - t0) * 1e3 / args.steps     # host wall clock: host-side work counts end to end
 
-    # ---- end-to-end through the CUDA-graph API (single GPU: same H2D / D2H per step, one graph launch)
-    e2e_graph_ms = None
+    e2e = {"fused_propagate_loss + backward": wall(step_e2e)}
+    # same step through the CUDA-graph API (single GPU: same H2D / D2H per step, one graph launch)
     if world == 1:
         gs = uq.GraphedFusedStep(B, L, M, dtype=rdt, loss="sharp", explicit_error=err_h is not None, sigma=wl["sigma"],
                                  seed=1234, device=dev, flags=flags)
-        for i in range(args.warmup):
-            gs(pulses_h, target_h, err_h)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            gs(pulses_h, target_h, err_h)
-        torch.cuda.synchronize()
-        e2e_graph_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e["GraphedFusedStep"] = wall(lambda i: gs(pulses_h, target_h, err_h))
+    # and through the target-chunked pipeline (copies and all-reduce of chunk n under the kernel of chunk n+1)
+    if err_h is None and px is None:
+        pe = pipe if pipe is not None else uq.PipelinedStep(B, L, M_total, chunks=4, dtype=rdt, sigma=wl["sigma"], seed=1234,
+                                                            group=group, device=dev, flags=flags)
+        e2e["PipelinedStep"] = wall(lambda i: pe(pulses_h, target_h, offset=i))
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the launch that was timed, against the oracle (rank 0; after the timed regions)
+    parity = None
+    if rank == 0 and rdt == torch.float32:
+        parity = parity_check(uq, ops, wl, pulses_d, tc, err_d, M, rank * M, args.warmup, flags, dev)
+
+    # ---- BASELINE config 3 (GRAPE, few targets) at THIS rank count: weak scaling in the sample axis, exchange named
+    c3 = config3(uq, ops, dev, group, rank, world)
+
     # ---- max over ranks
-    t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
+    e2e_best = min(e2e, key=e2e.get)
+    t = torch.tensor([step_ms, kern_ms] + [e2e[k] for k in sorted(e2e)], dtype=torch.float64, device=dev)
     if group is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    step_ms, kern_ms, e2e_ms = (float(x) for x in t.tolist())
+    vals = [float(x) for x in t.tolist()]
+    step_ms, kern_ms = vals[0], vals[1]
+    e2e = dict(zip(sorted(e2e), vals[2:]))
+    e2e_best = min(e2e, key=e2e.get)
+    e2e_ms = e2e[e2e_best]
 
     if rank == 0:
         props_step = float(B) * M_total * L
@@ -404,39 +425,45 @@ def main():
         if err_h is not None:
             h2d += err_h.numel() * err_h.element_size()
         d2h = grad_h.numel() * grad_h.element_size() + loss_h.element_size()
+        if e2e_best == "PipelinedStep":
+            d2h = (n_g + B) * grad_h.element_size()            # [G | Fsum] chunks
+        exchange = None
+        if group is not None:
+            exchange = ("nvlink peer memory, fused into the step" if px is not None else
+                        (f"nccl all-reduce per target chunk ({len(pipe.bounds)} chunks), overlapped with the next chunk's kernel"
+                         if pipe is not None else "nccl all-reduce"))
         line = {
             "metric": "SU(2) propagations/s fwd+bwd", "value": value, "unit": "prop/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": dict(workload_config(args.workload, B, L, M, M_total, world),
                            sincos="mufu" if args.fast_sincos else ("poly" if (args.flags & 4) else "table"),
-                           exchange=(None if group is None else ("nvlink peer memory, fused into the partials reduction"
-                                                                 if px is not None else "nccl all-reduce")),
-                           l2_flush_between_steps=True,
+                           exchange=exchange, l2_flush_between_steps=True,
                            timing="CUDA events per step on the launching stream, max over ranks"),
-            "e2e": {"value": props_step / (min(e2e_ms, e2e_graph_ms or e2e_ms) * 1e-3), "unit": "prop/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": min(e2e_ms, e2e_graph_ms or e2e_ms),
-                    "api": "GraphedFusedStep" if (e2e_graph_ms or 1e30) < e2e_ms else "fused_propagate_loss + backward",
-                    "autograd_api_ms": e2e_ms, "graph_api_ms": e2e_graph_ms,
+            "e2e": {"value": props_step / (e2e_ms * 1e-3), "unit": "prop/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": e2e_best,
+                    "ms_per_step_by_api": e2e,
+                    "result": ("loss + G = d(sum F)/d pulses (B, L, 2) + the scalar chain factor, on the host (d loss/d pulses = scale * G)"
+                               if e2e_best == "PipelinedStep" else "loss + d loss/d pulses (B, L, 2) on the host"),
                     "timing": "host wall clock around K steps, pinned host buffers in, pinned host buffers out"},
-            "gpu_launches": args.steps * (2 if world == 1 else (3 if px is not None else
-                                          2 + (1 if ops._lib.lib().uqoc_su2_workspace_bytes(B, L, M, 0, flags) > 0 else 0))),
+            "gpu_launches": n_launches,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s", "frac": ach_tflops / peak,
                          "traffic": ncu_dram_traffic(args.workload) if (rdt == torch.float32 and not args.flags and not args.fast_sincos) else None,
-                         "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_su2_fwdbwd_bench_launch_ncu.txt)",
+                         "traffic_unit": f"bytes per launch (ncu dram__bytes_read+write, profiles/{NCU_BENCH_PROFILE})",
                          "algorithmic_bytes_per_launch": float(B * L * 2 * 4 * 2 + B * 8 * 4 + B * 4),
                          "kernel": "su2_kernel_x2 (fused fwd+bwd, packed f32x2, table sin/cos)" if rdt == torch.float32 else "su2_kernel<double> (fused fwd+bwd)",
-                         "kernel_ms": kern_ms, "kernel_ms_includes_exchange": px is not None,
+                         "kernel_ms": kern_ms, "kernel_ms_includes_exchange": False,
                          "flop_per_prop": FLOP_PER_PROP_FWDBWD,
                          "peak_source": f"nominal FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure)",
                          "measured_ffma_tflops": peak_meas, "measured_ffma2_tflops": peak2},
-            "clocks": clocks, "loss": loss_val,
+            "clocks": clocks, "loss": loss_val, "parity_check": parity,
         }
+        line["other_configs"] = {"c3_grape_B1_L256_M65536_fwdbwd": c3}
         if world == 1:
             try:
-                line["other_configs"] = other_configs(uq, ops, dev)
+                line["other_configs"].update(other_configs(uq, ops, dev))
             except Exception as e:  # informative only
-                line["other_configs"] = {"error": repr(e)}
+                line["other_configs"]["error"] = repr(e)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, L)
             try:
@@ -447,6 +474,92 @@ def main():
     if group is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit(f"parity_check failed: {parity}")
+
+
+NCU_BENCH_PROFILE = "r2_su2_fwdbwd_bench_launch_ncu.txt"
+
+
+def parity_check(uq, ops, wl, pulses_d, tc, err_d, M, j0, offset, flags, dev, n_check: int = 8):
+    """Re-run the exact launch the timed region ran (same shape, plan, flags, Philox key) with the per-sample fidelities
+    and the errors it used written out, and compare `n_check` targets spread over the batch with the FP64 oracle
+    (oracle/uqoc_oracle.py, the checker) on THOSE errors.  Bounds: BASELINE.json's 1e-5 abs on F, 1e-4 rel on the gradient."""
+    import numpy as np
+    from oracle import uqoc_oracle as orc
+    B, L = wl["B"], wl["L"]
+    n_g = B * L * 2
+    buf = torch.empty(n_g + B, device=dev)
+    F = torch.empty(B * M, device=dev)
+    e_used = torch.empty(2, B * M, device=dev)
+    ops._launch_fwdbwd(pulses_d, tc, err_d, None, M, j0, wl["sigma"], 1234, offset, F, e_used, buf[n_g:], buf[:n_g], flags)
+    torch.cuda.synchronize()
+    sel = sorted(set(int(round(x)) for x in np.linspace(0, B - 1, n_check)))
+    U_t = wl["U_target"].numpy().astype(np.complex128)
+    p64 = wl["pulses"].numpy().astype(np.float32).astype(np.float64)
+    Fh = F.view(B, M)[sel].cpu().numpy()
+    Gh = buf[:n_g].view(B, L, 2)[sel].cpu().numpy()
+    Eh = e_used.view(2, B, M)[:, sel].cpu().numpy().astype(np.float64)
+    dF = dG = 0.0
+    for k, b in enumerate(sel):
+        _, G_b, F_b = orc.fidelity_sum_and_grad(p64[b:b + 1], U_t[b:b + 1], Eh[:, k], M)
+        dF = max(dF, float(np.abs(Fh[k] - F_b).max()))
+        dG = max(dG, float(np.abs(Gh[k] - G_b[0]).max() / np.abs(G_b[0]).max()))
+    return {"max_abs_dF": dF, "rel_dG": dG, "n": len(sel), "samples_per_target": M, "bounds": {"dF": 1e-5, "dG": 1e-4},
+            "ok": bool(dF < 1e-5 and dG < 1e-4),
+            "what": "the timed launch re-run with F_out / err_out; sampled targets vs oracle/uqoc_oracle.py (FP64) on the errors it used"}
+
+
+def config3(uq, ops, dev, group, rank, world):
+    """BASELINE config 3 (GRAPE: B = 1, L = 256, 65536 explicit eps PER GPU) as one library call per step, at this rank
+    count; the exchange of the 513-real vector is named.  CUDA events on the launching stream, max over ranks."""
+    wl = make_workload("grape", dev)
+    B, L, M = wl["B"], wl["L"], wl["M"]
+    p = wl["pulses"].to(dev)
+    tc = uq.target_coeffs(wl["U_target"].to(dev), torch.float32)
+    err = uq.philox_errors(B, M, wl["sigma"], 1, 0, j0=rank * M, device=dev)
+    buf = torch.empty(B * L * 2 + B, device=dev)
+    G, Fsum = buf[:B * L * 2], buf[B * L * 2:]
+    lo = torch.empty(3, device=dev)
+    px, exchange = None, None
+    if group is not None:
+        import torch.distributed as dist
+        try:
+            px = uq.PeerExchange(group, B, L, 2, torch.float32, dev)
+            exchange = "nvlink peer memory, fused into the step (uqoc_su2_fwdbwd_peer_loss)"
+        except Exception as e:  # no peer mapping on this box: still a GPU path
+            exchange = f"nccl all-reduce (PeerExchange unavailable: {e!r})"[:160]
+
+    def step():
+        if group is None:
+            ops._launch_fwdbwd_loss(p, tc, err, M, wl["sigma"], 1, 0, "sharp", 0.99, 100, None, None, Fsum, G, lo, 0)
+        elif px is not None:
+            ops._launch_fwdbwd_peer_loss(p, tc, err, M, rank * M, M * world, wl["sigma"], 1, 0, "sharp", 0.99, 100, None, None, Fsum, G,
+                                         lo, 0, px)
+        else:
+            ops._launch_fwdbwd(p, tc, err, None, M, rank * M, wl["sigma"], 1, 0, None, None, Fsum, G, 0)
+            dist.all_reduce(buf, group=group)
+            ops._finalize(Fsum, B * M * world, "sharp", 0.99, 100, G)
+
+    for _ in range(5):
+        step()
+    if group is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    iters = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms = float(t.item())
+    return {"prop_per_s": float(B) * M * world * L / (ms * 1e-3), "ms": ms, "n_gpus": world, "samples_per_gpu": M,
+            "exchange": exchange, "pct_fp32_peak_per_gpu": B * M * L * FLOP_PER_PROP_FWDBWD / (ms * 1e-3) / 74.45e12 * 100,
+            "loss": float(lo[0].item())}
 
 
 def ncu_dram_traffic(workload: str):
@@ -454,7 +567,9 @@ def ncu_dram_traffic(workload: str):
     `ncu --set full` capture of `tools/profile_fwdbwd.py 4096 4096 256` (profiles/r1_su2_fwdbwd_bench_launch_ncu.txt)."""
     if workload != "curriculum":
         return None
-    path = os.path.join(ROOT, "profiles", "r1_su2_fwdbwd_bench_launch_ncu.txt")
+    path = os.path.join(ROOT, "profiles", NCU_BENCH_PROFILE)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_su2_fwdbwd_bench_launch_ncu.txt")
     try:
         tot, units = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(path):
@@ -483,17 +598,6 @@ def other_configs(uq, ops, dev):
         return a.elapsed_time(b) / iters
 
     out = {}
-    for name, wlname in (("c3_grape_B1_L256_M65536_fwdbwd", "grape"),):
-        wl = make_workload(wlname, dev)
-        B, L, M = wl["B"], wl["L"], wl["M"]
-        p = wl["pulses"].to(dev)
-        tc = uq.target_coeffs(wl["U_target"].to(dev), torch.float32)
-        err = uq.philox_errors(B, M, wl["sigma"], 1, 0, device=dev)
-        buf = torch.empty(B * L * 2 + B, device=dev)
-        lo3 = torch.empty(3, device=dev)
-        ms = timed(lambda: ops._launch_fwdbwd_loss(p, tc, err, M, wl["sigma"], 1, 0, "sharp", 0.99, 100, None, None,
-                                                   buf[B * L * 2:], buf[:B * L * 2], lo3, 0))
-        out[name] = {"prop_per_s": B * M * L / (ms * 1e-3), "ms": ms}
     g = torch.Generator().manual_seed(0)
     L = 64
     pulse = torch.stack([(torch.rand(L, generator=g) * 2 - 1) * math.pi, 0.1 + 0.4 * torch.rand(L, generator=g)], -1).to(dev)

@@ -123,6 +123,16 @@ int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, c
                     void* workspace, int64_t workspace_bytes,
                     int dtype, unsigned flags, void* stream);
 
+/* Same for a SLICE of the targets: rows [b0, b0 + B) of a larger batch (pulses / target_c / outputs point at the slice).
+ * b0 only enters the Philox counter, so that a batch processed in target chunks -- chunk n's all-reduce and device-to-host
+ * copy overlapping chunk n+1's kernel -- draws exactly the samples of the un-chunked call. */
+int uqoc_su2_fwdbwd_slice(const void* pulses, const void* target_c, const void* err, const void* weight,
+                          int64_t B, int64_t L, int64_t M, int64_t j0, int64_t b0,
+                          double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                          void* F_out, void* err_out, void* Fsum, void* G,
+                          void* workspace, int64_t workspace_bytes,
+                          int dtype, unsigned flags, void* stream);
+
 /* ------------------------------------------------------------------------
  * Single-GPU training step in one call: uqoc_su2_fwdbwd followed by the loss epilogue of
  * uqoc_loss_finalize (n_total = B*M).  While the partial rows fit one block's bandwidth (few targets, e.g.

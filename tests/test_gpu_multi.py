@@ -98,6 +98,70 @@ def _worker(rank, world, port, ret):
     dist.broadcast(w0, 0)
     used_peer = any(isinstance(v, uq.PeerExchange) for v in t_multi.__dict__.get("_peer_cache", {}).values())
     out["trainer"] = ((w - m_single.net.weight.detach()).abs().max().item(), bool(torch.equal(w, w0)), used_peer)
+    # replicas with DROPOUT stay bit-identical: rank 0's CUDA RNG state (and parameters) are broadcast at construction
+    class TinyDrop(torch.nn.Module):
+        num_qubits = 1
+
+        def __init__(self):
+            super().__init__()
+            self.a, self.drop, self.b = torch.nn.Linear(4, 64), torch.nn.Dropout(0.3), torch.nn.Linear(64, 2 * L)
+
+        def forward(self, x):
+            y = torch.sigmoid(self.b(self.drop(torch.tanh(self.a(x))))).view(-1, L, 2)
+            return torch.stack([(y[..., 0] * 2 - 1) * 3.15, 0.1 + 0.4 * y[..., 1]], -1)
+
+    torch.manual_seed(100 + rank)                       # deliberately DIFFERENT seeds per rank before construction
+    torch.cuda.manual_seed(200 + rank)
+    m_drop = TinyDrop()
+    t_drop = FusedTrainer(m_drop, monte_carlo=M, device=dev, optimizer=torch.optim.Adam(m_drop.parameters(), lr=1e-2), seed=9,
+                          process_group=dist.group.WORLD)
+    for _ in range(4):
+        t_drop.train_epoch(emb, T, SigmaSpec(0.7, 0.05))
+    same = True
+    for prm in m_drop.parameters():
+        ref = prm.detach().clone()
+        dist.broadcast(ref, 0)
+        same = same and bool(torch.equal(ref, prm.detach()))
+    out["dropout_replicas_identical"] = same
+    # target-chunked pipelined step (all-reduce of chunk n under the kernel of chunk n+1) == the un-chunked single-GPU step
+    Bp, Lp, Mp = 37, 24, 900
+    pp = torch.stack([(torch.rand(Bp, Lp, generator=g) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(Bp, Lp, generator=g)], -1)
+    Tp = torch.matrix_exp(-1j * X[None] * (torch.rand(Bp, generator=g) * 3)[:, None, None])
+    pipe = uq.PipelinedStep(Bp, Lp, Mp, chunks=3, sigma=(0.7, 0.05), seed=5, group=dist.group.WORLD, device=dev)
+    val, Gp, scale, mfp = pipe(pp, Tp, offset=11)
+    lo = pipe.run_device(pp.to(dev), Tp.to(dev), offset=11)
+    p1 = pp.to(dev).requires_grad_(True)
+    loss1, mf1 = uq.fused_propagate_loss(p1, Tp.to(dev), monte_carlo=Mp, sigma=(0.7, 0.05), seed=5, offset=11)
+    loss1.backward()
+    gmax = p1.grad.abs().max().item()
+    g_host = (Gp * scale).to(dev)
+    g0 = pipe.gradient(pipe.d_out).clone()
+    dist.broadcast(g0, 0)
+    out["pipelined"] = (abs(val - loss1.item()) / abs(loss1.item()), ((g_host - p1.grad).abs().max() / gmax).item(),
+                        (mfp.to(dev) - mf1).abs().max().item(), abs(lo[0].item() - loss1.item()) / abs(loss1.item()),
+                        ((pipe.gradient(pipe.d_out) - p1.grad).abs().max() / gmax).item(),
+                        bool(torch.equal(g0, pipe.gradient(pipe.d_out))))
+    # peer-exchange soak: a few hundred back-to-back one-call steps over two shapes (few targets: fat blocks + dependent-
+    # launched exchange kernel; tiny: exchange inside the fused kernel's last block), every 25th checked against NCCL
+    soak_bad = 0
+    for (Bs, Ls, Ms) in ((1, 64, 16384), (3, 16, 400)):
+        pxs = uq.PeerExchange(dist.group.WORLD, Bs, Ls, 2, torch.float32, dev)
+        ps = torch.stack([(torch.rand(Bs, Ls, generator=g) * 2 - 1) * 3.15, 0.1 + 0.4 * torch.rand(Bs, Ls, generator=g)], -1).to(dev)
+        Ts = T[:Bs].to(dev)
+        for it in range(150):
+            pa = ps.clone().requires_grad_(True)
+            la, _ = uq.fused_propagate_loss(pa, Ts, monte_carlo=Ms, sigma=(0.7, 0.05), seed=6, offset=it, group=pxs)
+            la.backward()
+            if it % 25 == 0:
+                pb = ps.clone().requires_grad_(True)
+                lb, _ = uq.fused_propagate_loss(pb, Ts, monte_carlo=Ms, sigma=(0.7, 0.05), seed=6, offset=it, group=dist.group.WORLD)
+                lb.backward()
+                ga = pa.grad.clone()
+                dist.broadcast(ga, 0)
+                ok = (abs(la.item() - lb.item()) < 2e-5 * abs(lb.item()) and
+                      ((pa.grad - pb.grad).abs().max() / pb.grad.abs().max()).item() < 2e-5 and torch.equal(ga, pa.grad))
+                soak_bad += 0 if ok else 1
+    out["soak_bad"] = soak_bad
     ret[rank] = out
     dist.barrier()
     dist.destroy_process_group()
@@ -118,3 +182,7 @@ def test_sharded_fused_op_matches_single_gpu():
         for dl, dg, dmf, same in ret[rank]["peer"]:
             assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6, (rank, "peer", dl, dg, dmf)
             assert same, (rank, "peer")
+        assert ret[rank]["dropout_replicas_identical"], rank
+        dl, dg, dmf, dl_dev, dg_dev, same = ret[rank]["pipelined"]
+        assert dl < 2e-5 and dg < 2e-5 and dmf < 1e-6 and dl_dev < 2e-5 and dg_dev < 2e-5 and same, (rank, ret[rank]["pipelined"])
+        assert ret[rank]["soak_bad"] == 0, (rank, ret[rank]["soak_bad"])

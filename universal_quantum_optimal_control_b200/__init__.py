@@ -28,3 +28,4 @@ from .ops import (  # noqa: F401
 __version__ = "0.1.0"
 from .graphs import GraphedFusedStep  # noqa: F401,E402
 from .peer import PeerExchange  # noqa: F401,E402
+from .pipeline import PipelinedStep  # noqa: F401,E402

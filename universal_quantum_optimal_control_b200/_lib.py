@@ -29,6 +29,8 @@ SIGNATURES = {
     "uqoc_su2_workspace_bytes": (_i64, [_i64, _i64, _i64, _int, _uint]),
     "uqoc_su2_fwdbwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
                                _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
+    "uqoc_su2_fwdbwd_slice": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
+                                     _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_peer_data_bytes": (_i64, [_i64, _int, _int]),
     "uqoc_peer_flag_bytes": (_i64, [_int]),
     "uqoc_su2_fwdbwd_peer": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,

@@ -387,8 +387,9 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
                    int64_t M, int64_t j0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* U_out,
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
                    unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr,
-                   const LossSpec* ls = nullptr, const PeerSpec* peer = nullptr) {
+                   const LossSpec* ls = nullptr, const PeerSpec* peer = nullptr, int64_t b0 = 0) {
     Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
+    UQOC_CHECK_ARG(b0 >= 0 && b0 + B <= (1LL << 31), "target offset b0 out of range: %lld", (long long)b0);
     UQOC_CHECK_ARG((int64_t)B * plan.cps <= 0x7fffffffLL, "grid too large: %lld blocks", (long long)(B * plan.cps));
     UQOC_CHECK_ARG((flags & UQOC_FLAG_RNG_FROM_DEVICE) || offset <= 0xffffffffULL,
                    "Philox offset must be < 2^32 (it is one 32-bit counter word), got %llu", (unsigned long long)offset);
@@ -401,6 +402,7 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     p.B = (int)B; p.L = (int)L; p.M = (int)M;
     p.n_tiles = plan.n_tiles; p.splits = plan.splits; p.cps = plan.cps; p.C = plan.C;
     p.j0 = j0;
+    p.b0 = (int)b0;
     p.sig_d = (T)sig_d; p.sig_e = (T)sig_e;
     p.seed = seed; p.offset = offset;
     p.rng_dev = (flags & UQOC_FLAG_RNG_FROM_DEVICE) ? (const unsigned long long*)(uintptr_t)seed : nullptr;
@@ -547,6 +549,21 @@ int uqoc_su2_fwdbwd(const void* pulses, const void* target_c, const void* err, c
                                Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream);
     return su2_run<float>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
                           G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream);
+}
+
+int uqoc_su2_fwdbwd_slice(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
+                          int64_t M, int64_t j0, int64_t b0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* F_out,
+                          void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
+                          unsigned flags, void* stream) {
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && target_c && Fsum && G, "pulses, target_c, Fsum and G must be non-null");
+    if (dtype == UQOC_F64)
+        return su2_run<double>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out,
+                               Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, nullptr,
+                               nullptr, b0);
+    return su2_run<float>(pulses, target_c, err, weight, B, L, M, j0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
+                          G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, nullptr, nullptr, b0);
 }
 
 int64_t uqoc_peer_data_bytes(int64_t n, int world, int dtype) {

@@ -82,6 +82,7 @@ struct Su2Params {
     int cps;            // blocks per target: grid = B * cps, one partial [Fsum | G] per block
     int C;              // chunk length (padded to the gradient-buffer depth)
     long long j0;
+    int b0;             // global index of target 0 of this call (Philox counter word; target-chunked launches)
     T sig_d, sig_e;
     unsigned long long seed;
     unsigned long long offset;
@@ -133,7 +134,7 @@ __device__ __forceinline__ void su2_sample_errors(const Su2Params<T>& p, int b, 
         const T se = p.sig_tab != nullptr ? p.sig_tab[2 * b + 1] : p.sig_e;
         const unsigned long long seed = p.rng_dev != nullptr ? p.rng_dev[0] : p.seed;
         const unsigned offset = (unsigned)(p.rng_dev != nullptr ? p.rng_dev[1] : p.offset);   // host rejects >= 2^32
-        philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)b, seed, offset, sd, se, delta, eps);
+        philox_delta_eps<T>((uint64_t)(p.j0 + j), (uint32_t)(p.b0 + b), seed, offset, sd, se, delta, eps);
     }
 }
 

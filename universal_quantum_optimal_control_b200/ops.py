@@ -238,6 +238,14 @@ def _launch_fwdbwd(pulses, tc, error, weight, M, j0, sigma, seed, offset, F_out,
           _stream(pulses.device))
 
 
+def _launch_fwdbwd_slice(pulses, tc, error, M, j0, b0, sigma, seed, offset, Fsum, G, flags, ws=None):
+    """Rows [b0, b0 + B) of a larger batch: b0 only enters the Philox counter (target-chunked pipelines)."""
+    B, L, _ = pulses.shape
+    ws, ws_bytes = _ws_for(pulses, M, flags, ws)
+    _call("uqoc_su2_fwdbwd_slice", pulses.device, _ptr(pulses), _ptr(tc), _ptr(error), None, B, L, M, j0, b0, sigma[0], sigma[1],
+          seed, offset, None, None, _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes, _dt(pulses), flags, _stream(pulses.device))
+
+
 def _check_px(px, pulses):
     B, L, P = pulses.shape
     if not px.matches(B, L, P, pulses.dtype):

@@ -43,6 +43,23 @@ class SigmaSpec:
         return (self.delta_std, self.epsilon_std)
 
 
+def sync_replicas(model: torch.nn.Module, group, device) -> None:
+    """Sample sharding keeps the model REPLICATED: every rank runs the same forward / backward / optimiser step on
+    bit-identical ``[G | Fsum]`` (no parameter all-reduce).  That only holds if the replicas start identical and draw
+    the same dropout masks, so rank 0's parameters, buffers and CUDA RNG state are broadcast once at construction."""
+    import torch.distributed as dist
+    if group is None or dist.get_world_size(group) == 1:
+        return
+    dev = torch.device(device)
+    src = dist.get_global_rank(group, 0)
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src, group=group)
+    state = torch.cuda.get_rng_state(dev).to(dev)
+    dist.broadcast(state, src, group=group)
+    torch.cuda.set_rng_state(state.cpu(), dev)
+
+
 class FusedStepMixin:
     """train_epoch / evaluate of ``UniversalModelTrainer`` over the fused op."""
 
@@ -131,6 +148,8 @@ def fused_trainer_class(base):
                      compute_dtype: Optional[torch.dtype] = None, **kw):
             super().__init__(model, unitary_generator, error_sampler, fidelity_fn=fidelity_fn, loss_fn=loss_fn, **kw)
             self.fused_loss, self.fused_seed, self.fused_group, self.fused_dtype = loss, seed, process_group, compute_dtype
+            if process_group is not None:
+                sync_replicas(self.model, getattr(process_group, "group", process_group), self.device)
 
     FusedTrainer.__name__ = f"Fused{base.__name__}"
     return FusedTrainer
@@ -150,6 +169,8 @@ class FusedTrainer(FusedStepMixin):
         self.fused_loss, self.fused_seed, self.fused_group, self.fused_dtype = loss, seed, process_group, compute_dtype
         self.best_state = None
         self.best_fidelity = 0.0
+        if process_group is not None:
+            sync_replicas(self.model, getattr(process_group, "group", process_group), device)
 
     def train(self, train_inputs: torch.Tensor, train_unitaries: torch.Tensor, eval_inputs: torch.Tensor,
               eval_unitaries: torch.Tensor, error_params_list: List[Dict], epochs: int = 100, batch_size: int = 10,
