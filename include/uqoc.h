@@ -160,7 +160,10 @@ int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* e
  *   peer_data[q]  (HOST array, world entries): device address, valid in THIS process, of rank q's exchange
  *                 buffer of >= uqoc_peer_data_bytes(B + B*L*2, world, dtype) bytes (CUDA VMM / IPC peer mapping,
  *                 e.g. torch.distributed._symmetric_memory rendezvous -> buffer_ptrs)
+ *                 ZEROED once before first use (FP32: every exchanged real travels as an aligned 8-byte
+ *                 {value, epoch} word that the receiver polls - one NVLink latency, no fence / flag round trip)
  *   peer_flags[q] likewise, rank q's flag buffer of uqoc_peer_flag_bytes(world) bytes, zeroed once before first use
+ *                 (FP64 and the single-launch small-output path signal arrival through these flags)
  *   epoch         non-zero, the same on every rank, different from the previous call's (e.g. a call counter)
  * All ranks must make the same sequence of calls with the same (B, L, dtype); at most 16 ranks.  A rank whose
  * peers never make the matching call gives up after 10 s and returns NaN in Fsum / G (no hung GPU).

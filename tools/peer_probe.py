@@ -30,12 +30,19 @@ def step_peer(i):
     ops._launch_fwdbwd_peer(pulses, tc, None, M, rank * M, (1.0, 0.05), 7, i, None, None, Fsum, G, 0, px)
     return ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
 
+lo = torch.empty(3, device=dev)
+
+def step_peer_loss(i):
+    ops._launch_fwdbwd_peer_loss(pulses, tc, None, M, rank * M, M_total, (1.0, 0.05), 7, i, "sharp", 0.99, 100, None, None, Fsum, G,
+                                 lo, 0, px)
+    return lo
+
 def step_local(i):
     ops._launch_fwdbwd(pulses, tc, None, None, M, rank * M, (1.0, 0.05), 7, i, None, None, Fsum, G, 0)
     return ops._finalize(Fsum, B * M_total, "sharp", 0.99, 100, G)
 
 res = {}
-for name, fn in (("local(no exchange)", step_local), ("nccl", step_nccl), ("peer", step_peer)):
+for name, fn in (("local(no exchange)", step_local), ("nccl", step_nccl), ("peer", step_peer), ("peer+loss fused", step_peer_loss)):
     for i in range(5):
         fn(i)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -53,9 +60,9 @@ for name, fn in (("local(no exchange)", step_local), ("nccl", step_nccl), ("peer
         e0.record(); out = fn(i); e1.record(); torch.cuda.synchronize()
         lat.append(e0.elapsed_time(e1) * 1e3)
     lat.sort()
-    res[name] = (thr, lat[len(lat) // 2], float(out[0].item()))
+    res[name] = (thr, lat[len(lat) // 2], float(out[0].item()), float(G.abs().sum().item()))
 if rank == 0:
     for k, v in res.items():
-        print(f"{k:22s} back-to-back {v[0]:7.1f} us/step   aligned median {v[1]:7.1f} us   loss {v[2]:.6f}", flush=True)
+        print(f"{k:22s} back-to-back {v[0]:7.1f} us/step   aligned median {v[1]:7.1f} us   loss {v[2]:.6f}  sum|G| {v[3]:.6e}", flush=True)
 dist.barrier()
 dist.destroy_process_group()

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "uqoc_su2_kernels.cuh"
 #include "uqoc_su2_x2.cuh"
@@ -463,6 +464,14 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
         const long long cap = (long long)sm_count() * 2;          // 1024-thread blocks: 2 resident per SM
         if (blocks > cap) blocks = cap;
         if (blocks > kPeerMaxBlocks) blocks = kPeerMaxBlocks;
+        if constexpr (std::is_same<T, float>::value) {
+            // FP32: {value, epoch} words, no fence / flag round trip, loss epilogue in the same dependent launch
+            launch_dependent(su2_reduce_exchange_ll<32>, (unsigned)blocks, 1024, 0, stream, (const float*)p.Fsum_part,
+                             (const float*)p.G_part, plan.cps, (int)B, (long long)n_g, pp, ls ? ls->n_total : 1.0,
+                             ls ? ls->kind : -1, ls ? ls->tau : 0.0, ls ? ls->k : 0.0, (float*)Fsum, (float*)G,
+                             ls ? (float*)ls->loss_out : (float*)nullptr);
+            return launch_status("su2_reduce_exchange_ll");
+        }
         launch_dependent(su2_reduce_exchange<T, 32>, (unsigned)blocks, 1024, 0, stream, (const T*)p.Fsum_part, (const T*)p.G_part,
                          plan.cps, (int)B, (long long)n_g, pp, (T*)Fsum, (T*)G);
         rc = launch_status("su2_reduce_exchange");
@@ -568,7 +577,8 @@ int uqoc_su2_fwdbwd_slice(const void* pulses, const void* target_c, const void* 
 
 int64_t uqoc_peer_data_bytes(int64_t n, int world, int dtype) {
     if (n < 1 || world < 1) return 0;
-    return 2 * (int64_t)world * ((n + 31) / 32 * 32) * (dtype == UQOC_F64 ? 8 : 4);
+    (void)dtype;                // 8 bytes per exchanged real either way: FP64 values, or FP32 {value, epoch} words
+    return 2 * (int64_t)world * ((n + 31) / 32 * 32) * 8;
 }
 int64_t uqoc_peer_flag_bytes(int world) { return world < 1 ? 0 : (int64_t)world * kPeerMaxBlocks * (int64_t)sizeof(unsigned); }
 

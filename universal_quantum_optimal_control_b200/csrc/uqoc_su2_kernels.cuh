@@ -879,6 +879,143 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange(const T* __restri
     }
 }
 
+// ---- the same exchange with the data and its "arrived" mark in ONE 8-byte store (FP32) ---------------------------
+// su2_reduce_exchange pays two serialised NVLink transactions per call: the slot stores have to be fenced at system
+// scope before the flag may follow.  Here every exchanged real travels as {value, epoch} in one aligned 64-bit store
+// (delivered atomically), the receiver polls the word itself until it carries this call's epoch: one one-way NVLink
+// latency, no fence, no flag buffer.  The loss epilogue rides along: every block forms the pooled mean fidelity from
+// the B x world exchanged Fsum words in the same fixed order (bit-identical in every block and on every rank),
+// evaluates the loss and scales its gradient columns -- the multi-GPU step is main kernel + this one dependent launch.
+// Slot layout per rank buffer: u64 [2 sets][world][n_pad]; sets alternate with the epoch's parity (a rank can be at
+// most one call ahead of the slowest peer, see su2_reduce_exchange).  kind < 0: reduction + exchange only.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// poll one {value, epoch} word; false after 10 s (a peer never made the matching call)
+__device__ __forceinline__ bool ll_wait(const unsigned long long* p, unsigned epoch, float& val) {
+    unsigned long long w = ld_relaxed_sys_u64(p);
+    if ((int)((unsigned)(w >> 32) - epoch) < 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            w = ld_relaxed_sys_u64(p);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) return false;
+        } while ((int)((unsigned)(w >> 32) - epoch) < 0);
+    }
+    val = __uint_as_float((unsigned)w);
+    return true;
+}
+
+template <int YL>   // a template only so that the header can be included by several translation units
+__global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* __restrict__ Fsum_part, const float* __restrict__ G_part,
+                                                               int splits, int B, long long n_g, const PeerParams<float> pp,
+                                                               double n_total, int kind, double tau, double k,
+                                                               float* __restrict__ Fsum, float* __restrict__ G,
+                                                               float* __restrict__ loss_out) {
+    static_assert(YL == 32, "1024-thread blocks: one warp per part-lane / per peer");
+    __shared__ float red[YL][33];
+    __shared__ double fred[32];
+    __shared__ float s_scale;
+    __shared__ int s_timeout;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const long long n = n_g + B;
+    const long long n_groups = (n + 31) / 32;
+    const size_t set_off = (size_t)(pp.epoch & 1u) * pp.world * pp.n_pad;
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pp.data[pp.rank]) + set_off;
+    if (threadIdx.x == 0) s_timeout = 0;
+    grid_dependency_wait();
+    // ---- phase 1: reduce over the sample-tile partials, push {value, epoch} to every rank's slot[rank]
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long i = g * 32 + x;
+        float tot = 0.0f;
+        if (i < n_g) {
+#pragma unroll 8
+            for (int s = y; s < splits; s += YL) tot += G_part[(size_t)s * n_g + i];
+        } else if (i < n) {
+#pragma unroll 8
+            for (int s = y; s < splits; s += YL) tot += Fsum_part[(size_t)s * B + (i - n_g)];
+        }
+        red[y][x] = tot;
+        __syncthreads();
+        if (y == 0) {
+            float t = red[0][x];
+#pragma unroll
+            for (int yy = 1; yy < YL; ++yy) t += red[yy][x];
+            red[0][x] = t;
+        }
+        __syncthreads();
+        if (y < pp.world) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(pp.data[y]) + set_off + (size_t)pp.rank * pp.n_pad + i;
+            st_relaxed_sys_u64(dst, ((unsigned long long)pp.epoch << 32) | (unsigned long long)__float_as_uint(red[0][x]));
+        }
+        __syncthreads();
+    }
+    // ---- phase 2: wait for every rank's words of this block's outputs, sum the slots in rank order
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long i = g * 32 + x;
+        if (y < pp.world) {
+            float v = 0.0f;
+            if (!ll_wait(mine + (size_t)y * pp.n_pad + i, pp.epoch, v)) s_timeout = 1;
+            red[y][x] = v;
+        }
+        __syncthreads();
+        if (y == 0) {
+            float t = red[0][x];
+            for (int q = 1; q < pp.world; ++q) t += red[q][x];
+            if (s_timeout) t = NAN;
+            if (i < n_g) G[i] = t;                         // unscaled; scaled in place below by the same thread
+            else if (i < n) Fsum[i - n_g] = t;
+        }
+        __syncthreads();
+    }
+    if (kind < 0) return;
+    // ---- phase 3: pooled mean fidelity from ALL exchanged Fsum words (other blocks' columns included: polled here too,
+    // so no cross-block synchronisation), fixed order -> the same bits in every block and on every rank
+    {
+        double a = 0.0;
+        for (int b = threadIdx.x; b < B; b += 1024) {
+            float t = 0.0f;
+            for (int q = 0; q < pp.world; ++q) {
+                float v = 0.0f;
+                if (!ll_wait(mine + (size_t)q * pp.n_pad + n_g + b, pp.epoch, v)) s_timeout = 1;
+                t = (q == 0) ? v : t + v;
+            }
+            a += (double)t;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (x == 0) fred[y] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < 32; ++w) tot += fred[w];
+            double val, dval;
+            const double Fbar = tot / n_total;
+            su2_loss_eval(Fbar, kind, tau, k, val, dval);
+            s_scale = s_timeout ? NAN : (float)(dval / n_total);
+            if (blockIdx.x == 0 && loss_out != nullptr) {
+                loss_out[0] = s_timeout ? NAN : (float)val;
+                loss_out[1] = (float)Fbar;
+                loss_out[2] = (float)dval;
+            }
+        }
+        __syncthreads();
+    }
+    if (y == 0) {
+        const float sc = s_scale;
+        for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            const long long i = g * 32 + x;
+            if (i < n_g) G[i] *= sc;
+        }
+    }
+}
+
 template <typename T>
 inline void launch_reduce_partials(const T* Fsum_part, const T* G_part, int splits, int B, long long n_g, T* Fsum, T* G,
                                    cudaStream_t stream) {

@@ -169,7 +169,10 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
 #ifndef UQOC_X2_BWD_FORM
 #define UQOC_X2_BWD_FORM 0
 #endif
-constexpr int kFwdForm = UQOC_X2_FWD_FORM, kBwdForm = UQOC_X2_BWD_FORM;
+#ifndef UQOC_X2_BWD_ORDER
+#define UQOC_X2_BWD_ORDER 0      // 1 = reuse-ordered backward core (BWD_FORM 0 / 1 only)
+#endif
+constexpr int kFwdForm = UQOC_X2_FWD_FORM, kBwdForm = UQOC_X2_BWD_FORM, kBwdOrder = UQOC_X2_BWD_ORDER;
 // table entries staged for a kernel: interleaved {sin, cos} pairs and / or separate sin[] / cos[] arrays
 constexpr int x2_tab_il(bool table, bool bwd) {
     return !table ? 0 : ((bwd && kBwdForm >= 1) ? UQOC_SINCOS_TABLE_LEN : ((kFwdForm == 1) ? kTabN : 0));
@@ -230,8 +233,16 @@ __device__ __forceinline__ void sincos2_tab_il(F2 tau, const F2 (&kap)[NP], F2 (
         const int k0 = __float_as_int(f2lo(kf[u])), k1 = __float_as_int(f2hi(kf[u]));
         kb[2 * u] = FULL ? 0 : (k0 >> 10);
         kb[2 * u + 1] = FULL ? 0 : (k1 >> 10);
+#if defined(UQOC_X2_PROBE) && UQOC_X2_PROBE == 1      // timing probe (wrong results): conflict-free look-ups
+        T[2 * u].v = tsc[(k0 & 0) + (threadIdx.x & 31)];
+        T[2 * u + 1].v = tsc[(k1 & 0) + 32 + (threadIdx.x & 31)];
+#elif defined(UQOC_X2_PROBE) && UQOC_X2_PROBE == 2    // timing probe (wrong results): no look-ups at all
+        T[2 * u] = f2(__int_as_float(k0 & MASK) * 1e-9f, 1.0f);
+        T[2 * u + 1] = f2(__int_as_float(k1 & MASK) * 1e-9f, 1.0f);
+#else
         T[2 * u].v = tsc[k0 & MASK];
         T[2 * u + 1].v = tsc[k1 & MASK];
+#endif
     }
 #pragma unroll
     for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
@@ -269,7 +280,7 @@ __host__ __device__ inline size_t su2_x2_smem_bytes(int C, int wps, int st, bool
 #define UQOC_X2_MINB 5
 #endif
 #ifndef UQOC_X2_FWD_UNROLL
-#define UQOC_X2_FWD_UNROLL 2
+#define UQOC_X2_FWD_UNROLL 8
 #endif
 constexpr int kX2FwdUnroll = UQOC_X2_FWD_UNROLL;
 constexpr int kX2FatVB = 7;           // virtual blocks of the fat-block variant (NP = 1, WPS = 4): 896 threads x 72 registers
@@ -659,41 +670,69 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                                 s2[u] = mul2(sh, c[u]);              // sin 2h
                             }
                         }
+                        if constexpr (kBwdOrder == 1) {
+                            // one sample pair at a time, consecutive instructions sharing a register in the SAME operand
+                            // slot: ptxas flags it .reuse and the FFMA2 then reads two fresh register pairs instead of
+                            // three (tools/ubench/operand_ubench.cu: 2.2 instead of 3.06 cycles; core 2.44 vs 2.55)
+                            const F2 nsd = f2b(-row.y);
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {
-                            t[u] = fma2(kdl[u], W3[u], A[u]);
-                            uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
-                        }
+                            for (int u = 0; u < NP; ++u) {
+                                t[u] = fma2(kdl[u], W3[u], A[u]);
+                                uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                                Sr[u] = mul2(kr[u], s2[u]);
+                                k1_[u] = fma2(kr2[u], neg2(C2[u]), kr2[u]);
+                                B1[u] = mul2(Bq[u], C2[u]);
+                                BS[u] = mul2(Bq[u], Sr[u]);
+                                gp = fma2(Bq[u], Sr[u], gp);
+                                gt = fma2(t[u], kae[u], gt);
+                                K[u] = mul2(t[u], k1_[u]);
+                                gp = fma2(uu[u], neg2(k1_[u]), gp);
+                                B1[u] = fma2(uu[u], neg2(Sr[u]), B1[u]);
+                                Wz[u] = fma2(C2[u], W3[u], neg2(BS[u]));
+                                A1[u] = fma2(C2[u], A[u], K[u]);
+                                W3[u] = fma2(kdl[u], K[u], Wz[u]);
+                                A1[u] = fma2(kdl[u], BS[u], A1[u]);
+                                const F2 tA = mul2(A1[u], cd), tB = mul2(A1[u], sd);
+                                A[u] = fma2(B1[u], nsd, tA);
+                                Bq[u] = fma2(B1[u], cd, tB);
+                            }
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {
-                            Sr[u] = mul2(s2[u], kr[u]);
-                            gt = fma2(kae[u], t[u], gt);
-                        }
+                            for (int u = 0; u < NP; ++u) {
+                                t[u] = fma2(kdl[u], W3[u], A[u]);
+                                uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                            }
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {
-                            k1_[u] = fma2(neg2(C2[u]), kr2[u], kr2[u]);
-                            BS[u] = mul2(Bq[u], Sr[u]);
-                            B1[u] = mul2(Bq[u], C2[u]);
-                            gp = fma2(Sr[u], Bq[u], gp);
-                        }
+                            for (int u = 0; u < NP; ++u) {
+                                Sr[u] = mul2(s2[u], kr[u]);
+                                gt = fma2(kae[u], t[u], gt);
+                            }
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {
-                            K[u] = mul2(k1_[u], t[u]);
-                            gp = fma2(neg2(k1_[u]), uu[u], gp);
-                            B1[u] = fma2(neg2(uu[u]), Sr[u], B1[u]);
-                            Wz[u] = fma2(W3[u], C2[u], neg2(BS[u]));
-                        }
+                            for (int u = 0; u < NP; ++u) {
+                                k1_[u] = fma2(neg2(C2[u]), kr2[u], kr2[u]);
+                                BS[u] = mul2(Bq[u], Sr[u]);
+                                B1[u] = mul2(Bq[u], C2[u]);
+                                gp = fma2(Sr[u], Bq[u], gp);
+                            }
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {
-                            A1[u] = fma2(A[u], C2[u], K[u]);
-                            W3[u] = fma2(kdl[u], K[u], Wz[u]);
-                        }
+                            for (int u = 0; u < NP; ++u) {
+                                K[u] = mul2(k1_[u], t[u]);
+                                gp = fma2(neg2(k1_[u]), uu[u], gp);
+                                B1[u] = fma2(neg2(uu[u]), Sr[u], B1[u]);
+                                Wz[u] = fma2(W3[u], C2[u], neg2(BS[u]));
+                            }
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) A1[u] = fma2(kdl[u], BS[u], A1[u]);
+                            for (int u = 0; u < NP; ++u) {
+                                A1[u] = fma2(A[u], C2[u], K[u]);
+                                W3[u] = fma2(kdl[u], K[u], Wz[u]);
+                            }
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {
-                            A[u] = fma2(neg2(B1[u]), sd, mul2(A1[u], cd));
-                            Bq[u] = fma2(B1[u], cd, mul2(A1[u], sd));
+                            for (int u = 0; u < NP; ++u) A1[u] = fma2(kdl[u], BS[u], A1[u]);
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                A[u] = fma2(neg2(B1[u]), sd, mul2(A1[u], cd));
+                                Bq[u] = fma2(B1[u], cd, mul2(A1[u], sd));
+                            }
                         }
                         v[2 * e] = f2lo(gp) + f2hi(gp);
                         v[2 * e + 1] = f2lo(gt) + f2hi(gt);
