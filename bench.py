@@ -462,6 +462,8 @@ def main():
         if world == 1:
             try:
                 line["other_configs"].update(other_configs(uq, ops, dev))
+                if "su4" in line["other_configs"]:                # first-class block for the two-qubit path
+                    line["su4"] = line["other_configs"].pop("su4")
             except Exception as e:  # informative only
                 line["other_configs"]["error"] = repr(e)
         if not args.no_cpu_baseline:
@@ -581,6 +583,9 @@ def ncu_dram_traffic(workload: str):
         return None
 
 
+SU4_FLOP_PER_PROP = 1484.0      # executed FLOP per SU(4) (pulse, sample): 2 x 742 FMA-pipe lane operations (ncu)
+
+
 def other_configs(uq, ops, dev):
     """Device-side rates of the other BASELINE configs (parity-test cases, not the bench line): informative."""
     from universal_quantum_optimal_control_b200 import sweeps
@@ -613,6 +618,23 @@ def other_configs(uq, ops, dev):
     buf4 = torch.empty(B + B * L * 3, device=dev)
     ms = timed(lambda: ops._su4_launch(True, p4, tgt, None, None, M, 0, 1.0, (1.0, 0.05), 7, 0, None, None, None, buf4[:B], buf4[B:], 0), 5)
     out["c4_su4_B1_L128_M32768_fwdbwd"] = {"su4_prop_per_s": B * M * L / (ms * 1e-3), "ms": ms}
+    # the same launch shape with 8 targets (CZ-like target): enough blocks for every SM sub-partition
+    B8 = 8
+    p8 = p4.expand(B8, -1, -1).contiguous()
+    tgt8 = tgt.expand(B8, -1, -1, -1).contiguous()
+    buf8 = torch.empty(B8 + B8 * L * 3, device=dev)
+    ms8 = timed(lambda: ops._su4_launch(True, p8, tgt8, None, None, M, 0, 1.0, (1.0, 0.05), 7, 0, None, None, None, buf8[:B8], buf8[B8:], 0), 5)
+    fl = SU4_FLOP_PER_PROP
+    out["su4"] = {
+        "workload": "BASELINE config 4: two-qubit SU(4), L=128, M=32768 eps per target, fused fwd+bwd, eigenframe kernel, Philox eps on-chip",
+        "unit": "SU(4) prop/s", "B1": {"value": B * M * L / (ms * 1e-3), "ms": ms}, "B8": {"value": B8 * M * L / (ms8 * 1e-3), "ms": ms8},
+        "flop_per_prop": fl,
+        "flop_count": "EXECUTED: 2 x 742 FMA-pipe lane operations per (pulse, sample) (ncu instruction counts, "
+                      "profiles/r1_su4_eigenframe_fwdbwd_ncu.txt: 384 packed forward + ~358 backward / sin-cos); a dense "
+                      "per-pulse scaling-and-squaring formulation (UQOC_FLAG_SU4_PADE) executes 8160",
+        "roofline": {"bound": "fp32", "unit": "TFLOP/s", "peak": 74.44992,
+                     "achieved_B1": B * M * L * fl / (ms * 1e-3) / 1e12, "frac_B1": B * M * L * fl / (ms * 1e-3) / 74.44992e12,
+                     "achieved_B8": B8 * M * L * fl / (ms8 * 1e-3) / 1e12, "frac_B8": B8 * M * L * fl / (ms8 * 1e-3) / 74.44992e12}}
     # stock-torch-on-the-same-B200 (informative): the reference's ATen op sequence (oracle/torch_port.py) on cuda:0
     try:
         from oracle import torch_port as tp

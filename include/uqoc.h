@@ -245,6 +245,11 @@ int uqoc_su2_generator_backward(const void* pulses, const void* err, const void*
  *   H = 1/2 [cos phi1 XI + sin phi1 YI + cos phi2 IX + sin phi2 IY + delta1 ZI + delta2 IZ + J ZZ],
  *   U_k = exp(-i H_k tau_k (1+eps));  target (B, 4, 4) complex;  F = (|Tr(U^dagger T)|^2 + 4)/20
  *   G (B, L, 3) = sum_j weight * dF/d[phi1, phi2, tau];  U_out (B*M, 4, 4) complex.
+ * UQOC_FLAG_RNG_FROM_DEVICE works as for the SU(2) entry points (`seed` = device pointer to {seed, offset}).
+ * uqoc_su4_workspace_bytes fits forward and forward+backward launches of the shape alike.
+ * uqoc_su4_generator_backward is the autograd backward of the strict per-sample signature
+ * (pulses (Bm, L, 3), err (3, Bm), uqoc_su4_forward with B = Bm, M = 1 is its forward): grad_U (Bm, 4, 4) complex
+ * cotangent in torch's convention (dL = Re sum conj(g) dU) -> grad_pulses (Bm, L, 3).
  * ------------------------------------------------------------------------ */
 int64_t uqoc_su4_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags);
 int uqoc_su4_fwdbwd(const void* pulses, const void* target, const void* err, const void* weight,
@@ -257,6 +262,9 @@ int uqoc_su4_forward(const void* pulses, const void* target, const void* err,
                      double sig_d, double sig_e, uint64_t seed, uint64_t offset,
                      void* U_out, void* F_out, void* err_out, void* Fsum,
                      void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
+int uqoc_su4_generator_backward(const void* pulses, const void* err, const void* grad_U,
+                                int64_t Bm, int64_t L, double J, void* grad_pulses,
+                                int dtype, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------
  * Pulse heads: the element-wise tail of the two pulse generators, fused to

@@ -101,6 +101,6 @@ def test_python_flag_words_match_the_header():
     assert uq.tuning_flags(st=4, lps=8, splits=37) == (4 << 8) | (8 << 12) | (37 << 18)
     # peer-exchange sizing helpers are pure host functions
     lib = _lib.lib()
-    assert lib.uqoc_peer_data_bytes(513, 8, _lib.F32) == 2 * 8 * 544 * 4
+    assert lib.uqoc_peer_data_bytes(513, 8, _lib.F32) == 2 * 8 * 544 * 8     # {value, epoch} words: 8 bytes per real
     assert lib.uqoc_peer_flag_bytes(8) == 8 * 1024 * 4
     assert lib.uqoc_peer_data_bytes(0, 8, _lib.F32) == 0

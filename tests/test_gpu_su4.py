@@ -173,3 +173,100 @@ def test_su4_config4_sized_properties():
     l64, _ = uq.fused_propagate_loss_su4(p64, CZ, error=err_out.double(), monte_carlo=M, J=J)
     l64.backward()
     assert ((g1.double() - p64.grad).abs().max() / p64.grad.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
+def test_su4_generator_backward_matches_torch_autograd(dtype, tol):
+    """su4_unitary_generator is differentiable: an arbitrary real functional of U_out back-propagated through the
+    cotangent-seeded eigenframe kernel equals autograd through the matrix_exp + tree cross-oracle (complex128, CPU)."""
+    from oracle import torch_port as tp
+    Bm, L, J = 37, 19, 0.9
+    rng = np.random.default_rng(11)
+    pulses = np.stack([rng.uniform(-3.15, 3.15, (Bm, L)), rng.uniform(-3.15, 3.15, (Bm, L)), rng.uniform(0.1, 0.5, (Bm, L))], -1)
+    err = np.stack([rng.normal(0, 1.0, Bm), rng.normal(0, 1.0, Bm), rng.normal(0, 0.05, Bm)])
+    if dtype == torch.float32:
+        pulses, err = pulses.astype(np.float32).astype(np.float64), err.astype(np.float32).astype(np.float64)
+    Cw = rng.normal(size=(Bm, 4, 4)) + 1j * rng.normal(size=(Bm, 4, 4))
+    pr = torch.from_numpy(pulses).requires_grad_(True)
+    Ur = tp.su4_generator_tree(pr, torch.from_numpy(err), J)
+    lr = (torch.from_numpy(Cw).conj() * Ur).real.sum() + (Ur.abs() ** 4).sum()          # linear + non-linear part
+    lr.backward()
+    p = _t(pulses, dtype).requires_grad_(True)
+    U = uq.su4_unitary_generator(p, _t(err, dtype), J)
+    cdt = torch.complex128 if dtype == torch.float64 else torch.complex64
+    l = (_t(Cw).to(cdt).conj() * U).real.sum() + (U.abs() ** 4).sum()
+    l.backward()
+    assert (U.detach().cpu().to(torch.complex128) - Ur.detach()).abs().max().item() < (1e-12 if dtype == torch.float64 else 2e-5)
+    g, gr = p.grad.cpu().double(), pr.grad
+    assert ((g - gr).abs().max() / gr.abs().max()).item() < tol
+
+
+def test_su4_forward_only_fits_the_shape_workspace():
+    """the forward-only launch of a shape whose forward kernel would pick more splits than the backward kernel
+    used to fail with UQOC_E_WORKSPACE; the split count is now the same for both."""
+    L, J = 16, 1.0
+    for B in (100, 148 * 3, 148 * 5, 148 * 6 + 1, 1500):
+        M = 200
+        pulses, err, T = _case(B, B, L, M, J)
+        p = _t(pulses, torch.float32)
+        with torch.no_grad():
+            loss, mf = uq.fused_propagate_loss_su4(p, _t(T), monte_carlo=M, J=J, sigma=(0.5, 0.05), seed=3)
+        pg = p.clone().requires_grad_(True)
+        loss2, mf2 = uq.fused_propagate_loss_su4(pg, _t(T), monte_carlo=M, J=J, sigma=(0.5, 0.05), seed=3)
+        assert torch.allclose(mf, mf2, atol=2e-6), B
+        assert abs(loss.item() - loss2.item()) < 1e-5 * max(1.0, abs(loss2.item()))
+
+
+def test_su4_device_resident_philox_state():
+    """UQOC_FLAG_RNG_FROM_DEVICE for the SU(4) kernels: (seed, offset) read from device memory give the same step as
+    the immediate values (CUDA-graph replays advance the offset on the device)."""
+    B, L, M, J = 2, 12, 300, 1.0
+    pulses, err, T = _case(5, B, L, M, J)
+    for pade in PADE:
+        fl = uq.tuning_flags(su4_pade=pade)
+        p1 = _t(pulses, torch.float32).requires_grad_(True)
+        l1, f1 = uq.fused_propagate_loss_su4(p1, _t(T), monte_carlo=M, J=J, sigma=(0.7, 0.05), seed=17, offset=5, flags=fl)
+        l1.backward()
+        rng = torch.tensor([17, 5], dtype=torch.int64, device=DEV)
+        p2 = _t(pulses, torch.float32).requires_grad_(True)
+        l2, f2 = uq.fused_propagate_loss_su4(p2, _t(T), monte_carlo=M, J=J, sigma=(0.7, 0.05), seed=rng.data_ptr(), flags=fl | 8)
+        l2.backward()
+        assert torch.equal(f1, f2) and torch.equal(p1.grad, p2.grad) and l1.item() == l2.item()
+
+
+def test_su4_graphed_train_step_matches_eager():
+    """GraphedTrainStep with a 3-parameter pulse model (two-qubit path): replays reproduce the eager FusedTrainer-style
+    steps (same Philox offsets, Adam, clipping)."""
+    from universal_quantum_optimal_control_b200.trainer import GraphedTrainStep, SigmaSpec
+    B, L, M = 4, 10, 256
+
+    class Tiny2Q(torch.nn.Module):
+        num_qubits = 2
+
+        def __init__(self):
+            super().__init__()
+            self.net = torch.nn.Linear(6, 3 * L)
+
+        def forward(self, x):
+            y = self.net(x).view(-1, L, 3)
+            return torch.stack([3.0 * torch.tanh(y[..., 0]), 3.0 * torch.tanh(y[..., 1]), 0.1 + 0.4 * torch.sigmoid(y[..., 2])], -1)
+
+    torch.manual_seed(0)
+    m_g, m_e = Tiny2Q().to(DEV), Tiny2Q().to(DEV)
+    m_e.load_state_dict(m_g.state_dict())
+    emb = torch.randn(B, 6, device=DEV)
+    _, _, T = _case(2, B, L, 1, 1.0)
+    Tt = _t(T).to(torch.complex64)
+    step = GraphedTrainStep(m_g, B=B, emb_shape=(6,), monte_carlo=M, lr=1e-2, seed=9, target_dim=4)
+    opt = torch.optim.Adam(m_e.parameters(), lr=1e-2)
+    spec = SigmaSpec(0.6, 0.05)
+    for it in range(1, 4):
+        lg = step(emb, Tt, spec).item()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = uq.fused_propagate_loss_su4(m_e(emb), Tt, monte_carlo=M, sigma=spec.sigma, seed=9, offset=it)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m_e.parameters(), max_norm=1.0)
+        opt.step()
+        assert abs(lg - loss.item()) < 1e-5 * max(1.0, abs(loss.item())), (it, lg, loss.item())
+    for a, b in zip(m_g.parameters(), m_e.parameters()):
+        assert torch.allclose(a, b, atol=1e-5)

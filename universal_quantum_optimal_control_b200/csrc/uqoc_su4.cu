@@ -189,7 +189,15 @@ struct Su4Params {
     T* err_out;    // (3, B*M)
     T* Fsum_part;  // [splits][B]
     T* G_part;     // [splits][B][L][3]
+    const unsigned long long* rng_dev;   // non-null: {seed, offset} read from device memory (CUDA-graph replay)
+    const T* cot;  // non-null (eigenframe backward only): per-sample cotangent dLoss/dU (B*M, 4, 4, 2) seeds the adjoint
 };
+// Philox (seed, offset) of a launch: immediate values or the device-resident pair of UQOC_FLAG_RNG_FROM_DEVICE
+template <typename T>
+__device__ __forceinline__ void su4_rng_state(const Su4Params<T>& p, unsigned long long& seed, unsigned& offset) {
+    seed = p.rng_dev != nullptr ? p.rng_dev[0] : p.seed;
+    offset = p.rng_dev != nullptr ? (unsigned)p.rng_dev[1] : p.offset;
+}
 
 template <typename T>
 __device__ __forceinline__ void philox_su4(uint64_t j, uint32_t b, uint64_t seed, uint32_t offset, T sig_d, T sig_e,
@@ -272,7 +280,9 @@ __global__ void __launch_bounds__(kSu4Threads) su4_kernel(const Su4Params<T> p) 
                 if (p.err != nullptr) {
                     d1 = p.err[sidx]; d2 = p.err[Bm + sidx]; eps = p.err[2 * Bm + sidx];
                 } else {
-                    philox_su4<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, d1, d2, eps);
+                    unsigned long long seed; unsigned offset;
+                    su4_rng_state(p, seed, offset);
+                    philox_su4<T>((uint64_t)(p.j0 + j), (uint32_t)b, seed, offset, p.sig_d, p.sig_e, d1, d2, eps);
                 }
                 if (p.err_out != nullptr) {
                     p.err_out[sidx] = d1; p.err_out[Bm + sidx] = d2; p.err_out[2 * Bm + sidx] = eps;
@@ -397,6 +407,8 @@ static int su4_blocks_per_sm(K kern, size_t smem) {
     return n;
 }
 
+// The split count is taken from the BACKWARD kernel's occupancy for forward launches too: one workspace size
+// (uqoc_su4_workspace_bytes) then fits every launch of a shape, whichever kernel it is.
 static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags, bool bwd) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
@@ -408,12 +420,11 @@ static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fla
     if (pade) pl.smem = f64 ? su4_smem_bytes<double>((int)L, bwd) : su4_smem_bytes<float>((int)L, bwd);
     else pl.smem = f64 ? su4e_smem_bytes<double>((int)L, bwd) : su4e_smem_bytes<float>((int)L, bwd);
     int occ;
-    if (pade) {
-        occ = f64 ? (bwd ? su4_blocks_per_sm(su4_kernel<double, true>, pl.smem) : su4_blocks_per_sm(su4_kernel<double, false>, pl.smem))
-                  : (bwd ? su4_blocks_per_sm(su4_kernel<float, true>, pl.smem) : su4_blocks_per_sm(su4_kernel<float, false>, pl.smem));
-    } else {
-        occ = f64 ? (bwd ? su4_blocks_per_sm(su4e_kernel<double, true>, pl.smem) : su4_blocks_per_sm(su4e_kernel<double, false>, pl.smem))
-                  : (bwd ? su4_blocks_per_sm(su4e_kernel<float, true>, pl.smem) : su4_blocks_per_sm(su4e_kernel<float, false>, pl.smem));
+    {
+        const size_t smem_b = pade ? (f64 ? su4_smem_bytes<double>((int)L, true) : su4_smem_bytes<float>((int)L, true))
+                                   : (f64 ? su4e_smem_bytes<double>((int)L, true) : su4e_smem_bytes<float>((int)L, true));
+        if (pade) occ = f64 ? su4_blocks_per_sm(su4_kernel<double, true>, smem_b) : su4_blocks_per_sm(su4_kernel<float, true>, smem_b);
+        else occ = f64 ? su4_blocks_per_sm(su4e_kernel<double, true, false>, smem_b) : su4_blocks_per_sm(su4e_kernel<float, true, false>, smem_b);
     }
     pl.n_tiles = (int)((M + kSu4Threads - 1) / kSu4Threads);
     // one wave: at most sms*occ blocks; every block of a target walks `rounds` tiles (the last may walk one less)
@@ -433,13 +444,18 @@ template <typename T, bool BWD>
 static int su4_run(const void* pulses, const void* target, const void* err, const void* weight, int64_t B, int64_t L,
                    int64_t M, int64_t j0, double J, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* U_out,
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
-                   unsigned flags, cudaStream_t stream) {
+                   unsigned flags, cudaStream_t stream, const void* cot = nullptr) {
     const Su4Plan pl = su4_plan(B, L, M, dtype, flags, BWD);
+    UQOC_CHECK_ARG(B * (int64_t)pl.splits <= 0x7fffffffLL, "grid too large: %lld blocks", (long long)(B * pl.splits));
+    UQOC_CHECK_ARG((flags & UQOC_FLAG_RNG_FROM_DEVICE) || offset <= 0xffffffffULL,
+                   "Philox offset must be < 2^32 (it is one 32-bit counter word), got %llu", (unsigned long long)offset);
     Su4Params<T> p;
     p.pulses = (const T*)pulses; p.target = (const T*)target; p.err = (const T*)err; p.weight = (const T*)weight;
     p.B = (int)B; p.L = (int)L; p.M = (int)M; p.n_tiles = pl.n_tiles; p.splits = pl.splits;
     p.j0 = j0; p.J = (T)J; p.sig_d = (T)sig_d; p.sig_e = (T)sig_e; p.seed = seed; p.offset = (unsigned)offset;
     p.U_out = (T*)U_out; p.F_out = (T*)F_out; p.err_out = (T*)err_out;
+    p.rng_dev = (flags & UQOC_FLAG_RNG_FROM_DEVICE) ? (const unsigned long long*)(uintptr_t)seed : nullptr;
+    p.cot = (const T*)cot;
     const int64_t n_g = BWD ? B * L * 3 : 0;
     if (pl.splits > 1) {
         const int64_t need = (int64_t)pl.splits * (B + n_g) * (int64_t)sizeof(T);
@@ -454,7 +470,10 @@ static int su4_run(const void* pulses, const void* target, const void* err, cons
         p.G_part = (T*)G;
     }
     static_assert(kSu4Threads == kSu4eThreads, "both SU(4) kernels share the launch plan");
-    auto kern = (flags & UQOC_FLAG_SU4_PADE) ? su4_kernel<T, BWD> : su4e_kernel<T, BWD>;
+    auto kern = (flags & UQOC_FLAG_SU4_PADE) ? su4_kernel<T, BWD> : su4e_kernel<T, BWD, false>;
+    if constexpr (BWD) {
+        if (cot != nullptr) kern = su4e_kernel<T, true, true>;      // cotangent-seeded adjoint: eigenframe kernel only
+    }
     if (pl.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         if (e != cudaSuccess) {
@@ -521,6 +540,22 @@ int uqoc_su4_forward(const void* pulses, const void* target, const void* err, in
                                       err_out, Fsum, nullptr, workspace, workspace_bytes, dtype, flags, (cudaStream_t)stream);
     return su4_run<float, false>(pulses, target, err, nullptr, B, L, M, j0, J, sig_d, sig_e, seed, offset, U_out, F_out, err_out,
                                  Fsum, nullptr, workspace, workspace_bytes, dtype, flags, (cudaStream_t)stream);
+}
+
+/* backward of the strict generator signature: pulses (Bm, L, 3) one row PER SAMPLE, err (3, Bm), gU = dLoss/dU
+ * (Bm, 4, 4, 2) in torch's convention for complex tensors (dLoss = Re sum conj(gU) dU) -> g_pulses (Bm, L, 3).
+ * One block per sample row (correct, not tuned: the fused entry points are the fast path). */
+int uqoc_su4_generator_backward(const void* pulses, const void* err, const void* gU, int64_t Bm, int64_t L, double J,
+                                void* g_pulses, int dtype, unsigned flags, void* stream) {
+    int rc = su4_check(Bm, L, 1, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(pulses && err && gU && g_pulses, "pulses, err, gU and g_pulses must be non-null");
+    flags &= ~(unsigned)(UQOC_FLAG_SU4_PADE | UQOC_FLAG_RNG_FROM_DEVICE);
+    if (dtype == UQOC_F64)
+        return su4_run<double, true>(pulses, gU /* unused target */, err, nullptr, Bm, L, 1, 0, J, 0, 0, 0, 0, nullptr, nullptr,
+                                     nullptr, nullptr, g_pulses, nullptr, 0, dtype, flags, (cudaStream_t)stream, gU);
+    return su4_run<float, true>(pulses, gU, err, nullptr, Bm, L, 1, 0, J, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                                g_pulses, nullptr, 0, dtype, flags, (cudaStream_t)stream, gU);
 }
 
 }  // extern "C"

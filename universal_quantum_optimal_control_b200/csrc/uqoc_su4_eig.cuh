@@ -441,8 +441,11 @@ __host__ __device__ inline size_t su4e_smem_bytes(int L, bool bwd) {
 #ifndef UQOC_SU4E_MINB
 #define UQOC_SU4E_MINB 6
 #endif
-template <typename T, bool BWD>
+// COT (backward only): the adjoint is seeded from a per-sample cotangent dLoss/dU (p.cot) instead of the fidelity
+// against the target -- the backward of the strict generator signature (uqoc_su4_generator_backward).
+template <typename T, bool BWD, bool COT>
 __global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? UQOC_SU4E_MINB : 1) su4e_kernel(const Su4Params<T> p) {
+    static_assert(BWD || !COT, "the cotangent seed belongs to the backward kernel");
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int L = p.L;
     T* tab = reinterpret_cast<T*>(smem_raw);                // {sin[1024] | cos[1024]} of k pi/1024
@@ -499,9 +502,13 @@ __global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? UQOC_SU4E_MINB 
             const double gam = (i == 0) ? 0.5 * (p1 + p2) : (i == 1) ? 0.5 * (p1 - p2) : (i == 2) ? -0.5 * (p1 - p2) : -0.5 * (p1 + p2);
             double sg, cg;
             ::sincos(gam, &sg, &cg);
-            const double tr_ = (double)p.target[(size_t)b * 32 + 2 * tid], ti_ = (double)p.target[(size_t)b * 32 + 2 * tid + 1];
-            tgt[2 * tid] = (T)(cg * tr_ - sg * ti_);
-            tgt[2 * tid + 1] = (T)(cg * ti_ + sg * tr_);
+            if constexpr (!COT) {
+                const double tr_ = (double)p.target[(size_t)b * 32 + 2 * tid], ti_ = (double)p.target[(size_t)b * 32 + 2 * tid + 1];
+                tgt[2 * tid] = (T)(cg * tr_ - sg * ti_);
+                tgt[2 * tid + 1] = (T)(cg * ti_ + sg * tr_);
+            } else {
+                tgt[2 * tid] = tgt[2 * tid + 1] = (T)0;
+            }
             if ((tid & 3) == 0) {
                 rl[2 * i] = (T)cg;
                 rl[2 * i + 1] = (T)sg;
@@ -524,7 +531,9 @@ __global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? UQOC_SU4E_MINB 
                 if (p.err != nullptr) {
                     d1 = p.err[sidx]; d2 = p.err[Bm + sidx]; eps = p.err[2 * Bm + sidx];
                 } else {
-                    philox_su4<T>((uint64_t)(p.j0 + j), (uint32_t)b, p.seed, p.offset, p.sig_d, p.sig_e, d1, d2, eps);
+                    unsigned long long seed; unsigned offset;
+                    su4_rng_state(p, seed, offset);
+                    philox_su4<T>((uint64_t)(p.j0 + j), (uint32_t)b, seed, offset, p.sig_d, p.sig_e, d1, d2, eps);
                 }
                 if (p.err_out != nullptr) {
                     p.err_out[sidx] = d1; p.err_out[Bm + sidx] = d2; p.err_out[2 * Bm + sidx] = eps;
@@ -640,22 +649,49 @@ __global__ void __launch_bounds__(kSu4eThreads, sizeof(T) == 4 ? UQOC_SU4E_MINB 
             if (valid) wgt = p.weight != nullptr ? p.weight[sidx] : (T)1;
             Herm4<T> A;
             {
-                const T fr = wgt * trr * (T)0.1, fi = wgt * tri * (T)0.1;
                 T cr_[4][4], ci_[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
+                if constexpr (COT) {
+                    // C = Q gU'^dagger with gU' = R_L^dagger gU (row i times e^{+i gamma_i}); an invalid slot contributes 0
+                    const T* gu = p.cot + sidx * 32;
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        T mr = (T)0, mi = (T)0;
+                        const T cg = rl[2 * jj], sg = rl[2 * jj + 1];
+                        T t_r[4], t_i[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const T t_r = tgt[2 * (4 * jj + k)], t_i = tgt[2 * (4 * jj + k) + 1];
-                            mr += qr[i][k] * t_r + qi[i][k] * t_i;
-                            mi += qi[i][k] * t_r - qr[i][k] * t_i;
+                            const T g_r = valid ? gu[2 * (4 * jj + k)] : (T)0, g_i = valid ? gu[2 * (4 * jj + k) + 1] : (T)0;
+                            t_r[k] = cg * g_r - sg * g_i;
+                            t_i[k] = cg * g_i + sg * g_r;
                         }
-                        cr_[i][jj] = fr * mr - fi * mi;
-                        ci_[i][jj] = fr * mi + fi * mr;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            T mr = (T)0, mi = (T)0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                mr += qr[i][k] * t_r[k] + qi[i][k] * t_i[k];
+                                mi += qi[i][k] * t_r[k] - qr[i][k] * t_i[k];
+                            }
+                            cr_[i][jj] = mr;
+                            ci_[i][jj] = mi;
+                        }
                     }
+                } else {
+                    const T fr = wgt * trr * (T)0.1, fi = wgt * tri * (T)0.1;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            T mr = (T)0, mi = (T)0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const T t_r = tgt[2 * (4 * jj + k)], t_i = tgt[2 * (4 * jj + k) + 1];
+                                mr += qr[i][k] * t_r + qi[i][k] * t_i;
+                                mi += qi[i][k] * t_r - qr[i][k] * t_i;
+                            }
+                            cr_[i][jj] = fr * mr - fi * mi;
+                            ci_[i][jj] = fr * mi + fi * mr;
+                        }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     A.dg[i] = ci_[i][i];

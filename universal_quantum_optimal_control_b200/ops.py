@@ -607,6 +607,14 @@ def _su4_target(U_target: torch.Tensor, rdt: torch.dtype, B: int) -> torch.Tenso
     return torch.view_as_real(U_target.to(cdt).resolve_conj().contiguous()).contiguous()
 
 
+def su4_workspace(B: int, L: int, M: int, dtype: torch.dtype, flags: int, device) -> torch.Tensor:
+    """A private workspace for one (B, L, M) SU(4) launch shape (CUDA-graph owners)."""
+    dev = torch.device(device)
+    with _on_device(dev):
+        n = int(_lib.lib().uqoc_su4_workspace_bytes(B, L, M, F64 if dtype == torch.float64 else F32, flags))
+    return alloc_workspace(n, dev)
+
+
 def _su4_launch(bwd, pulses, tgt, error, weight, M, j0, J, sigma, seed, offset, U_out, F_out, err_out, Fsum, G, flags, ws=None):
     B, L, _ = pulses.shape
     dt = _dt(pulses)
@@ -615,6 +623,8 @@ def _su4_launch(bwd, pulses, tgt, error, weight, M, j0, J, sigma, seed, offset, 
         ws_bytes = int(_lib.lib().uqoc_su4_workspace_bytes(B, L, M, dt, flags))
     if ws is None:
         ws = _workspace(ws_bytes, dev)
+    elif ws.numel() < ws_bytes:
+        raise ValueError(f"workspace of {ws.numel()} bytes is too small for this launch shape ({ws_bytes} bytes)")
     if bwd:
         _call("uqoc_su4_fwdbwd", dev, _ptr(pulses), _ptr(tgt), _ptr(error), _ptr(weight), B, L, M, j0, float(J), float(sigma[0]),
               float(sigma[1]), seed, offset, _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(ws), ws_bytes, dt, flags,
@@ -627,13 +637,14 @@ def _su4_launch(bwd, pulses, tgt, error, weight, M, j0, J, sigma, seed, offset, 
 
 class _FusedPropagateLossSU4(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pulses, tgt, error, M, j0, M_total, J, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out):
+    def forward(ctx, pulses, tgt, error, M, j0, M_total, J, sigma, seed, offset, loss, tau, k, flags, group, F_out, err_out,
+                ws=None):
         B, L, _ = pulses.shape
         need_grad = ctx.needs_input_grad[0]
         n_g = B * L * 3 if need_grad else 0
         buf = torch.empty(n_g + B, dtype=pulses.dtype, device=pulses.device)
         G, Fsum = (buf[:n_g] if need_grad else None), buf[n_g:]
-        _su4_launch(need_grad, pulses, tgt, error, None, M, j0, J, sigma, seed, offset, None, F_out, err_out, Fsum, G, flags)
+        _su4_launch(need_grad, pulses, tgt, error, None, M, j0, J, sigma, seed, offset, None, F_out, err_out, Fsum, G, flags, ws)
         if group is not None:
             import torch.distributed as dist
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
@@ -647,16 +658,18 @@ class _FusedPropagateLossSU4(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_mean):
         (G,) = ctx.saved_tensors
-        return (g_loss * G,) + (None,) * 16
+        return (g_loss * G,) + (None,) * 17
 
 
 def fused_propagate_loss_su4(pulses: torch.Tensor, U_target: torch.Tensor, *, error: Optional[torch.Tensor] = None,
                              monte_carlo: int, J: float = 1.0, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0,
                              offset: int = 0, loss: str = "sharp", tau: float = 0.99, k: float = 100,
                              dtype: Optional[torch.dtype] = None, flags: int = 0, group=None,
-                             F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None):
+                             F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None,
+                             workspace: Optional[torch.Tensor] = None):
     """Two-qubit twin of :func:`fused_propagate_loss`: pulses (B, L, 3) = [phi1, phi2, tau], U_target (B, 4, 4),
-    error (3, B*M) = [delta1; delta2; eps] or None (Philox), coupling ``J`` of the ZZ term."""
+    error (3, B*M) = [delta1; delta2; eps] or None (Philox), coupling ``J`` of the ZZ term.  ``workspace``: a private
+    buffer from :func:`su4_workspace` for callers that capture the launch in a CUDA graph."""
     if pulses.ndim != 3 or pulses.shape[-1] != 3:
         raise ValueError("'pulses' must have shape (B, L, 3)")
     _require_cuda(pulses, "pulses")
@@ -678,13 +691,41 @@ def fused_propagate_loss_su4(pulses: torch.Tensor, U_target: torch.Tensor, *, er
         error = shard_errors(error.to(rdt), B, M_total, j0, M).contiguous()
     return _FusedPropagateLossSU4.apply(pulses.to(rdt).contiguous(), tgt, error, M, j0, M_total, float(J),
                                         tuple(float(x) for x in sigma), int(seed), int(offset), loss, tau, k, flags, group,
-                                        F_out, err_out)
+                                        F_out, err_out, workspace)
+
+
+class _GeneratorSU4(torch.autograd.Function):
+    """Per-sample pulse rows: forward = uqoc_su4_forward with B = Bm, M = 1; backward = uqoc_su4_generator_backward."""
+
+    @staticmethod
+    def forward(ctx, pulses, err, J, flags):
+        Bm = pulses.shape[0]
+        rdt = pulses.dtype
+        cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+        U = torch.empty(Bm, 4, 4, 2, dtype=rdt, device=pulses.device)
+        tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None].expand(Bm, -1, -1), rdt, Bm)
+        _su4_launch(False, pulses, tgt, err, None, 1, 0, J, (0.0, 0.0), 0, 0, U, None, None, None, None, flags)
+        ctx.save_for_backward(pulses, err)
+        ctx.args = (J, flags)
+        return torch.view_as_complex(U)
+
+    @staticmethod
+    def backward(ctx, gU):
+        pulses, err = ctx.saved_tensors
+        J, flags = ctx.args
+        Bm, L, _ = pulses.shape
+        g = torch.view_as_real(gU.resolve_conj()).to(pulses.dtype).contiguous()
+        gp = torch.empty_like(pulses)
+        _call("uqoc_su4_generator_backward", pulses.device, _ptr(pulses), _ptr(err), _ptr(g), Bm, L, float(J), _ptr(gp),
+              _dt(pulses), flags, _stream(pulses.device))
+        return gp, None, None, None
 
 
 def su4_unitary_generator(pulses: torch.Tensor, error: torch.Tensor, J: float = 1.0, flags: int = 0) -> torch.Tensor:
     """Two-qubit generator with the reference's calling convention: pulses (Bm, L, 3), error (3, Bm) ->
-    (Bm, 4, 4) complex.  Forward only.  ``expand``-ed (stride-0) pulses share one staged pulse train;
-    materialised per-sample rows are run one target per block (correct, not tuned)."""
+    (Bm, 4, 4) complex, differentiable w.r.t. ``pulses`` (one block per sample row: correct, not tuned -- the fused
+    :func:`fused_propagate_loss_su4` is the fast path).  ``expand``-ed (stride-0) pulses that need no gradient share one
+    staged pulse train."""
     if pulses.ndim != 3 or pulses.shape[-1] != 3:
         raise ValueError("'pulses' must have shape (B, L, 3)")
     _require_cuda(pulses, "pulses")
@@ -694,17 +735,15 @@ def su4_unitary_generator(pulses: torch.Tensor, error: torch.Tensor, J: float = 
         raise ValueError(f"'error' must have shape (3, {Bm})")
     rdt = torch.float64 if (pulses.dtype == torch.float64 or error.dtype == torch.float64) else torch.float32
     cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
-    U = torch.empty(Bm, 4, 4, 2, dtype=rdt, device=pulses.device)
     err = error.to(rdt).contiguous()
-    if Bm > 1 and pulses.stride(0) == 0:
+    grad_needed = pulses.requires_grad and torch.is_grad_enabled()
+    if Bm > 1 and pulses.stride(0) == 0 and not grad_needed:
+        U = torch.empty(Bm, 4, 4, 2, dtype=rdt, device=pulses.device)
         tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None], rdt, 1)
         _su4_launch(False, pulses[0:1].to(rdt).contiguous(), tgt, err, None, Bm, 0, J, (0.0, 0.0), 0, 0, U, None, None, None,
                     None, flags)
-    else:
-        tgt = _su4_target(torch.eye(4, dtype=cdt, device=pulses.device)[None].expand(Bm, -1, -1), rdt, Bm)
-        _su4_launch(False, pulses.to(rdt).contiguous(), tgt, err, None, 1, 0, J, (0.0, 0.0), 0, 0, U, None, None, None, None,
-                    flags)
-    return torch.view_as_complex(U)
+        return torch.view_as_complex(U)
+    return _GeneratorSU4.apply(pulses.to(rdt).contiguous(), err, float(J), int(flags) & ~64)   # eigenframe kernel both ways
 
 
 def philox_errors_su4(B: int, M: int, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, offset: int = 0, j0: int = 0,

@@ -241,11 +241,13 @@ class GraphedTrainStep:
         fn = ops.fused_propagate_loss_su4 if pulses.shape[-1] == 3 else ops.fused_propagate_loss
         kw = dict(monte_carlo=self.M, sigma=sigma, seed=self.d_rng.data_ptr(), loss=self.loss, dtype=self.dtype,
                   flags=self.flags | 8)                               # 8 = UQOC_FLAG_RNG_FROM_DEVICE
-        if pulses.shape[-1] == 3:
-            raise NotImplementedError("device-resident Philox state is wired for the SU(2) kernels only")
         if self._ws is None:                                          # first warm-up step, outside capture
-            self._ws = ops.su2_workspace(pulses.shape[0], pulses.shape[1], self.M, self.dtype or torch.float32,
-                                         kw["flags"] | ops.FLAG_RAW_TARGET, self.device)
+            if pulses.shape[-1] == 3:
+                self._ws = ops.su4_workspace(pulses.shape[0], pulses.shape[1], self.M, self.dtype or torch.float32, kw["flags"],
+                                             self.device)
+            else:
+                self._ws = ops.su2_workspace(pulses.shape[0], pulses.shape[1], self.M, self.dtype or torch.float32,
+                                             kw["flags"] | ops.FLAG_RAW_TARGET, self.device)
         loss, fid = fn(pulses, self.s_target, workspace=self._ws, **kw)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
@@ -291,7 +293,8 @@ class GraphedTrainStep:
         self.s_emb.copy_(U_emb, non_blocking=True)
         self.s_target.copy_(U_target, non_blocking=True)
         self._stream.wait_stream(torch.cuda.current_stream(self.device))
-        graph.replay()
+        with torch.cuda.stream(self._stream):                         # CUDAGraph.replay() launches on the CURRENT stream
+            graph.replay()
         torch.cuda.current_stream(self.device).wait_stream(self._stream)
         return self.s_loss
 
