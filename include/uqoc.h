@@ -281,6 +281,24 @@ int uqoc_pulse_head_backward(const void* logits, const void* base_pulse, const v
                              int mode, const double* ranges, double scale, void* grad_logits, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * The same heads FOLDED INTO the fused step (SURVEY.md §8f row f-3 as specified): the head runs while the fused
+ * kernel stages the pulse train and its backward while the gradient rows are written, so the whole
+ *   logits -> pulses -> Monte-Carlo propagation -> fidelity -> loss -> d loss / d logits
+ * of model/universal_model.py:131-143 (or model/GRAPE_model.py:76-89) + trainer.py:80-90 is the fused kernel and its
+ * epilogue; no (B, L, 2) pulses tensor is exchanged between model and op.
+ *   logits (B, L, 2) head_mode 0 | (B, L, 3) head_mode 1;  ranges / scale / phi_offset / base_pulse as above
+ *   G (B, L, 2 | 3) = d loss / d logits (loss_kind >= 0) or d(sum_j F)/d logits (loss_kind = -1); G = NULL: forward only
+ *   pulses_out (B, L, 2) nullable: the pulses the head produced (logging, trainer.py:260-266)
+ *   loss_out (3) as uqoc_loss_finalize;  errors explicit (2, B*M) or Philox (err = NULL);  workspace as uqoc_su2_fwdbwd
+ * ------------------------------------------------------------------------ */
+int uqoc_su2_head_step(const void* logits, int head_mode, const double* ranges, double scale, const void* phi_offset,
+                       const void* base_pulse, const void* target_c, const void* err,
+                       int64_t B, int64_t L, int64_t M, double sig_d, double sig_e, uint64_t seed, uint64_t offset,
+                       int loss_kind, double tau, double k,
+                       void* pulses_out, void* F_out, void* err_out, void* Fsum, void* G, void* loss_out,
+                       void* workspace, int64_t workspace_bytes, int dtype, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------
  * Loss epilogue (SCORE.py:185-198 applied to the pooled mean, and the chain rule
  * of loss.backward() at trainer.py:90):
  *   Fbar = sum_b Fsum[b] / n_total;  loss_out[0] = loss(Fbar); loss_out[1] = Fbar;

@@ -10,6 +10,7 @@ from .ops import (  # noqa: F401
     custom_loss,
     fidelity,
     fp32_peak_tflops,
+    fused_head_propagate_loss,
     fused_propagate_loss,
     fused_propagate_loss_su4,
     philox_errors_su4,

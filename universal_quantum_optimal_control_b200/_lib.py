@@ -55,6 +55,8 @@ SIGNATURES = {
     "uqoc_su4_generator_backward": (_int, [_vp, _vp, _vp, _i64, _i64, _dbl, _vp, _int, _uint, _vp]),
     "uqoc_pulse_head_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.POINTER(_dbl), _dbl, _vp, _int, _vp]),
     "uqoc_pulse_head_backward": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.POINTER(_dbl), _dbl, _vp, _int, _vp]),
+    "uqoc_su2_head_step": (_int, [_vp, _int, C.POINTER(_dbl), _dbl, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _dbl, _dbl, _u64, _u64,
+                                  _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _uint, _vp]),
     "uqoc_loss_finalize": (_int, [_vp, _i64, _dbl, _int, _dbl, _dbl, _vp, _i64, _vp, _int, _vp]),
     "uqoc_fidelity_forward": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _vp]),
     "uqoc_fidelity_backward": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _int, _vp]),

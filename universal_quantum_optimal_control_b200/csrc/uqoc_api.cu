@@ -383,12 +383,21 @@ struct PeerSpec {
     unsigned epoch;
 };
 
+// pulse head folded into the op (uqoc_su2_head_step): host-side description
+struct HeadArgs {
+    int mode;                 // 1 transformer head (logits (B, L, 2)), 2 GRAPE head (logits (B, L, 3))
+    double lo0, hi0, lo1, hi1, scale;
+    const void* offset;       // (B) or null
+    const void* base;         // (L, 2) or null
+    void* pulses_out;         // (B, L, 2) or null
+};
+
 template <typename T>
 static int su2_run(const void* pulses, const void* target_c, const void* err, const void* weight, int64_t B, int64_t L,
                    int64_t M, int64_t j0, double sig_d, double sig_e, uint64_t seed, uint64_t offset, void* U_out,
                    void* F_out, void* err_out, void* Fsum, void* G, void* workspace, int64_t workspace_bytes, int dtype,
                    unsigned flags, bool bwd, cudaStream_t stream, int grid_ne = 0, const void* sig_tab = nullptr,
-                   const LossSpec* ls = nullptr, const PeerSpec* peer = nullptr, int64_t b0 = 0) {
+                   const LossSpec* ls = nullptr, const PeerSpec* peer = nullptr, int64_t b0 = 0, const HeadArgs* head = nullptr) {
     Su2Plan plan = make_plan(B, L, M, dtype, flags, bwd);
     UQOC_CHECK_ARG(b0 >= 0 && b0 + B <= (1LL << 31), "target offset b0 out of range: %lld", (long long)b0);
     UQOC_CHECK_ARG((int64_t)B * plan.cps <= 0x7fffffffLL, "grid too large: %lld blocks", (long long)(B * plan.cps));
@@ -410,7 +419,14 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     p.U_out = (T*)U_out; p.F_out = (T*)F_out; p.err_out = (T*)err_out;
     p.grid_ne = grid_ne; p.sig_tab = (const T*)sig_tab;
     p.raw_target = (flags & UQOC_FLAG_RAW_TARGET) ? 1 : 0;
-    const int64_t n_g = bwd ? B * L * 2 : 0;
+    if (head != nullptr) {
+        p.head.mode = head->mode;
+        p.head.lo0 = (T)head->lo0; p.head.hi0 = (T)head->hi0; p.head.lo1 = (T)head->lo1; p.head.hi1 = (T)head->hi1;
+        p.head.scale = (T)head->scale;
+        p.head.offset = (const T*)head->offset; p.head.base = (const T*)head->base; p.head.pulses_out = (T*)head->pulses_out;
+    }
+    const int po = su2_grad_width(p);                      // reals per pulse of a gradient row (3 for the GRAPE head's logits)
+    const int64_t n_g = bwd ? B * L * po : 0;
     const int64_t part_bytes = plan.cps > 1 ? (int64_t)plan.cps * (B + n_g) * (int64_t)sizeof(T) : 0;
     if (plan.cps > 1) {
         if (workspace == nullptr || workspace_bytes < kTicketBytes + part_bytes) {
@@ -427,7 +443,7 @@ static int su2_run(const void* pulses, const void* target_c, const void* err, co
     const bool want_fin = bwd && Fsum != nullptr && (ls != nullptr || peer != nullptr || plan.cps > 1);
     plan.fin = want_fin && !(flags & UQOC_FLAG_NO_FIN) && workspace != nullptr && workspace_bytes >= kTicketBytes &&
                ((uintptr_t)workspace % 16 == 0) && ((uintptr_t)G % (4 * sizeof(T)) == 0) &&
-               su2_fin_supported(B, L, plan.cps, (plan.packed ? kThreads * plan.vb : kThreads));
+               su2_fin_supported(B, L, plan.cps, (plan.packed ? kThreads * plan.vb : kThreads), po);
     if (plan.fin) {
         p.fin.ticket = (unsigned*)workspace;
         p.fin.Fsum = (T*)Fsum;
@@ -541,7 +557,8 @@ int64_t uqoc_su2_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, uns
     if (B < 1 || L < 1 || M < 1) return 0;
     const int64_t esz = dtype == UQOC_F64 ? 8 : 4;
     const Su2Plan pb = make_plan(B, L, M, dtype, flags, true), pf = make_plan(B, L, M, dtype, flags, false);
-    const int64_t nb = pb.cps > 1 ? (int64_t)pb.cps * (B + B * L * 2) * esz : 0;      // fused fwd+bwd: [Fsum | G] rows
+    const int64_t nb = pb.cps > 1 ? (int64_t)pb.cps * (B + B * L * 3) * esz : 0;      // fused fwd+bwd: [Fsum | G] rows (3 reals
+                                                                                      // per pulse: the GRAPE head's logit rows)
     const int64_t nf = pf.cps > 1 ? (int64_t)pf.cps * B * esz : 0;                    // forward only: Fsum rows
     return kTicketBytes + (nb > nf ? nb : nf);
 }
@@ -640,6 +657,33 @@ int uqoc_su2_fwdbwd_loss(const void* pulses, const void* target_c, const void* e
                                Fsum, G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, &ls);
     return su2_run<float>(pulses, target_c, err, nullptr, B, L, M, 0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
                           G, workspace, workspace_bytes, dtype, flags, true, (cudaStream_t)stream, 0, nullptr, &ls);
+}
+
+int uqoc_su2_head_step(const void* logits, int head_mode, const double* ranges, double scale, const void* phi_offset,
+                       const void* base_pulse, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M,
+                       double sig_d, double sig_e, uint64_t seed, uint64_t offset, int loss_kind, double tau, double k,
+                       void* pulses_out, void* F_out, void* err_out, void* Fsum, void* G, void* loss_out, void* workspace,
+                       int64_t workspace_bytes, int dtype, unsigned flags, void* stream) {
+    int rc = check_common(B, L, M, dtype);
+    if (rc) return rc;
+    UQOC_CHECK_ARG(logits && target_c && Fsum && ranges, "logits, ranges, target_c and Fsum must be non-null");
+    UQOC_CHECK_ARG(head_mode == 0 || head_mode == 1, "head_mode must be 0 (transformer) or 1 (GRAPE), got %d", head_mode);
+    UQOC_CHECK_ARG(loss_kind >= -1 && loss_kind <= 3, "unknown loss kind %d", loss_kind);
+    UQOC_CHECK_ARG(loss_kind < 0 || loss_out != nullptr, "loss_out must be non-null when a loss is requested");
+    UQOC_CHECK_ARG(head_mode == 0 || (phi_offset == nullptr && base_pulse == nullptr), "the GRAPE head takes no offset / base pulse");
+    const HeadArgs head{head_mode + 1, ranges[0], ranges[1], ranges[2], ranges[3], scale, phi_offset, base_pulse, pulses_out};
+    LossSpec ls{(double)B * (double)M, tau, k, loss_kind, loss_out};
+    const bool bwd = G != nullptr;
+    if (dtype == UQOC_F64)
+        rc = su2_run<double>(logits, target_c, err, nullptr, B, L, M, 0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
+                             G, workspace, workspace_bytes, dtype, flags, bwd, (cudaStream_t)stream, 0, nullptr,
+                             (bwd && loss_kind >= 0) ? &ls : nullptr, nullptr, 0, &head);
+    else
+        rc = su2_run<float>(logits, target_c, err, nullptr, B, L, M, 0, sig_d, sig_e, seed, offset, nullptr, F_out, err_out, Fsum,
+                            G, workspace, workspace_bytes, dtype, flags, bwd, (cudaStream_t)stream, 0, nullptr,
+                            (bwd && loss_kind >= 0) ? &ls : nullptr, nullptr, 0, &head);
+    if (rc || bwd || loss_kind < 0) return rc;
+    return uqoc_loss_finalize(Fsum, B, ls.n_total, loss_kind, tau, k, nullptr, 0, loss_out, dtype, stream);   // forward only
 }
 
 int uqoc_su2_forward(const void* pulses, const void* target_c, const void* err, int64_t B, int64_t L, int64_t M, int64_t j0,

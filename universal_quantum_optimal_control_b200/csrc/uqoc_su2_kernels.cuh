@@ -71,9 +71,28 @@ struct FinParams {
     PeerParams<T> pp;
 };
 
+// ---- pulse heads folded into the op ----------------------------------------------------
+// The element-wise tail of the reference's pulse generators is applied while the pulse train is staged, and its
+// backward while the gradient rows are written: no (B, L, 2) pulses tensor travels between model and op, and the
+// 6-8 small ATen launches per direction of model/universal_model.py:131-143 / model/GRAPE_model.py:76-89 disappear.
+//   mode 1 (transformer head): u = sigmoid(x); p = lo + (hi - lo) u; [p = scale p + base]; tau = relu(tau);
+//                              phi = wrap(phi + offset_b) to [-pi, pi)                       logits (B, L, 2)
+//   mode 2 (GRAPE head):       (ux, uy, ut) = sigmoid(x); phi = lo0 + (hi0 - lo0) atan2(uy, ux);
+//                              tau = relu(lo1 + (hi1 - lo1) ut)                              logits (B, L, 3)
+template <typename T>
+struct HeadSpec {
+    int mode;          // 0: `pulses` holds the pulses themselves
+    T lo0, hi0, lo1, hi1, scale;
+    const T* offset;   // (B) target azimuth or nullptr            (mode 1)
+    const T* base;     // (L, 2) finetune base pulse or nullptr    (mode 1)
+    T* pulses_out;     // (B, L, 2) or nullptr: the pulses the head produced (for logging / saving)
+};
+template <typename T>
+__device__ __forceinline__ T head_sigmoid(T v) { return (T)1 / ((T)1 + exp(-v)); }
+
 template <typename T>
 struct Su2Params {
-    const T* pulses;    // (B, L, 2)
+    const T* pulses;    // (B, L, 2), or the head's logits (B, L, 2 | 3) when head.mode != 0
     const T* target_c;  // (B, 8)
     const T* err;       // (2, B*M) or nullptr (Philox)
     const T* weight;    // (B*M) or nullptr
@@ -97,7 +116,69 @@ struct Su2Params {
     const T* sig_tab;     // non-null: per-target (sigma_delta, sigma_eps) rows for the Philox samples
     int raw_target;       // != 0: target_c holds the raw complex targets (B, 2, 2, 2) (UQOC_FLAG_RAW_TARGET)
     FinParams<T> fin;
+    HeadSpec<T> head;
 };
+
+// reals per pulse of the gradient rows: the head's input width
+template <typename T>
+__host__ __device__ __forceinline__ int su2_grad_width(const Su2Params<T>& p) { return p.head.mode == 2 ? 3 : 2; }
+
+// (phi, tau) of pulse i of target b: the stored pulse, or the head applied to its logits (same arithmetic as the
+// stand-alone pulse_head_kernel, csrc/uqoc_api.cu)
+template <typename T>
+__device__ __forceinline__ void su2_pulse_at(const Su2Params<T>& p, int b, int i, T& phi, T& tau) {
+    const HeadSpec<T>& h = p.head;
+    if (h.mode == 0) {
+        const T* pb = p.pulses + ((size_t)b * p.L + i) * 2;
+        phi = pb[0];
+        tau = pb[1];
+    } else if (h.mode == 1) {
+        const T PI = (T)3.14159265358979323846;
+        const T* x = p.pulses + ((size_t)b * p.L + i) * 2;
+        const T u0 = head_sigmoid(x[0]), u1 = head_sigmoid(x[1]);
+        T ph = h.lo0 + (h.hi0 - h.lo0) * u0, ta = h.lo1 + (h.hi1 - h.lo1) * u1;
+        if (h.base != nullptr) {
+            ph = h.scale * ph + h.base[2 * i];
+            ta = h.scale * ta + h.base[2 * i + 1];
+        }
+        ta = ta > (T)0 ? ta : (T)0;
+        if (h.offset != nullptr) ph += h.offset[b];
+        T m = fmod(ph + PI, (T)2 * PI);                    // python's float modulo: the result has the divisor's sign
+        if (m < (T)0) m += (T)2 * PI;
+        phi = m - PI;
+        tau = ta;
+    } else {
+        const T* x = p.pulses + ((size_t)b * p.L + i) * 3;
+        const T ux = head_sigmoid(x[0]), uy = head_sigmoid(x[1]), ut = head_sigmoid(x[2]);
+        const T ta = h.lo1 + (h.hi1 - h.lo1) * ut;
+        phi = h.lo0 + (h.hi0 - h.lo0) * atan2(uy, ux);
+        tau = ta > (T)0 ? ta : (T)0;
+    }
+}
+// gradient row of pulse i w.r.t. the head's inputs from (d/dphi, d/dtau); returns the row width
+template <typename T>
+__device__ __forceinline__ int su2_head_grad(const Su2Params<T>& p, int b, int i, T gphi, T gtau, T (&o)[3]) {
+    const HeadSpec<T>& h = p.head;
+    if (h.mode == 1) {
+        const T* x = p.pulses + ((size_t)b * p.L + i) * 2;
+        const T u0 = head_sigmoid(x[0]), u1 = head_sigmoid(x[1]);
+        T ta = h.lo1 + (h.hi1 - h.lo1) * u1;
+        if (h.base != nullptr) ta = h.scale * ta + h.base[2 * i + 1];
+        const T sc = h.base != nullptr ? h.scale : (T)1;
+        o[0] = gphi * sc * (h.hi0 - h.lo0) * u0 * ((T)1 - u0);
+        o[1] = ta > (T)0 ? gtau * sc * (h.hi1 - h.lo1) * u1 * ((T)1 - u1) : (T)0;
+        o[2] = (T)0;
+        return 2;
+    }
+    const T* x = p.pulses + ((size_t)b * p.L + i) * 3;
+    const T ux = head_sigmoid(x[0]), uy = head_sigmoid(x[1]), ut = head_sigmoid(x[2]);
+    const T ta = h.lo1 + (h.hi1 - h.lo1) * ut;
+    const T g = gphi * (h.hi0 - h.lo0) / (ux * ux + uy * uy);
+    o[0] = g * (-uy) * ux * ((T)1 - ux);
+    o[1] = g * ux * uy * ((T)1 - uy);
+    o[2] = ta > (T)0 ? gtau * (h.hi1 - h.lo1) * ut * ((T)1 - ut) : (T)0;
+    return 3;
+}
 
 // trace coefficients of target b: Tr(U^dagger T) = (cr + i ci) . q.  Either precomputed rows (uqoc_su2_target_coeffs)
 // or formed here from the raw 2x2 complex target: c0 = T00+T11, c1 = i(T01+T10), c2 = T10-T01, c3 = i(T00-T11).
@@ -259,7 +340,8 @@ __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
 #endif
 template <typename T>
 __device__ UQOC_FIN_ATTR void su2_block_finalize(const FinParams<T>& f, const T* __restrict__ G_part, const T* __restrict__ Fsum_part,
-                                                 const int parts, const int B, const int L, unsigned char* scr_raw) {
+                                                 const int parts, const int B, const int L, unsigned char* scr_raw,
+                                                 const int po = 2 /* reals per pulse of a gradient row */) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     double* dred = reinterpret_cast<double*>(scr_raw);                       // [40]: warp sums, scale, flags
     T* red = reinterpret_cast<T*>(scr_raw + 40 * sizeof(double));            // [nthr][4] part-lane partials
@@ -282,7 +364,7 @@ __device__ UQOC_FIN_ATTR void su2_block_finalize(const FinParams<T>& f, const T*
 #ifdef UQOC_FIN_TIMING
     if (tid == 0) { stamp[0] = ts_enter; stamp[1] = now(); }
 #endif
-    const int n_g = B * L * 2, ncol4 = n_g / 4, ncol = ncol4 + B;
+    const int n_g = B * L * po, ncol4 = n_g / 4, ncol = ncol4 + B;
     int Y = nthr / ncol;                                           // part-lanes per column
     if (Y > parts) Y = parts;
     const int cpp = nthr / Y;                                      // columns per part-lane (>= ncol)
@@ -407,8 +489,8 @@ __device__ UQOC_FIN_ATTR void su2_block_finalize(const FinParams<T>& f, const T*
 }
 // bytes of shared scratch su2_block_finalize needs for a block of `nthr` threads, and the launch shapes it supports
 __host__ __device__ inline size_t su2_fin_smem_bytes(int nthr, size_t elem) { return 40 * sizeof(double) + (size_t)nthr * 5 * elem; }
-__host__ __device__ inline bool su2_fin_supported(long long B, long long L, int parts, int nthr) {
-    const long long n_g = B * L * 2, ncol = n_g / 4 + B;
+__host__ __device__ inline bool su2_fin_supported(long long B, long long L, int parts, int nthr, int po = 2) {
+    const long long n_g = B * L * po, ncol = n_g / 4 + B;
     // <= 4 16-byte loads per thread: beyond that one block's pass over the partial rows (measured 11 us for the 148 rows
     // of BASELINE config 3) loses to a dependent-launched reduction kernel spread over many SMs (5.7 us)
     return (n_g % 4 == 0) && ncol <= nthr && (long long)parts * ncol <= 4LL * nthr;
@@ -457,13 +539,19 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
 
     // ---- stage the target's pulse train: coalesced loads, trig in double, rounded once ----
     {
-        const T* pb = p.pulses + (size_t)b * L * 2;
         for (int i = tid; i < LPS * C; i += kThreads) {
             const int ic = i < L ? i : L - 1;
             const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
-            const double phi = (double)pb[2 * ic];
-            const double phim = (double)pb[2 * im];
-            const T tau = i < L ? pb[2 * ic + 1] : (T)0;
+            T ph_c, ta_c, ph_m, ta_m;
+            su2_pulse_at<T>(p, b, ic, ph_c, ta_c);
+            su2_pulse_at<T>(p, b, im, ph_m, ta_m);
+            if (p.head.pulses_out != nullptr && split == 0 && i < L) {
+                p.head.pulses_out[((size_t)b * L + i) * 2] = ph_c;
+                p.head.pulses_out[((size_t)b * L + i) * 2 + 1] = ta_c;
+            }
+            const double phi = (double)ph_c;
+            const double phim = (double)ph_m;
+            const T tau = i < L ? ta_c : (T)0;
             double sn, cs;
             ::sincos(phi, &sn, &cs);
             const int row = i + i / C;
@@ -688,18 +776,35 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
         p.Fsum_part[(size_t)split * p.B + b] = tot;
     }
     if constexpr (BWD) {
-        T* gout = p.G_part + ((size_t)split * p.B + b) * L * 2;
         const int LC2 = LPS * C * 2;
-        for (int i = tid; i < 2 * L; i += kThreads) {
-            T tot = (T)0;
+        if (p.head.mode == 0) {
+            T* gout = p.G_part + ((size_t)split * p.B + b) * L * 2;
+            for (int i = tid; i < 2 * L; i += kThreads) {
+                T tot = (T)0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
-            gout[i] = (i & 1) ? tot : tot * (T)0.5;   // d/dphi carries the 1/2 of sin 2h = 2 s c
+                for (int w = 0; w < kWarps; ++w) tot += acc[(size_t)w * LC2 + i];
+                gout[i] = (i & 1) ? tot : tot * (T)0.5;   // d/dphi carries the 1/2 of sin 2h = 2 s c
+            }
+        } else {
+            // head backward: one thread per pulse, (d/dphi, d/dtau) -> the head's input row
+            const int po = su2_grad_width(p);
+            T* gout = p.G_part + ((size_t)split * p.B + b) * L * po;
+            for (int l = tid; l < L; l += kThreads) {
+                T t0 = (T)0, t1 = (T)0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) {
+                    t0 += acc[(size_t)w * LC2 + 2 * l];
+                    t1 += acc[(size_t)w * LC2 + 2 * l + 1];
+                }
+                T o[3];
+                su2_head_grad<T>(p, b, l, t0 * (T)0.5, t1, o);
+                for (int c = 0; c < po; ++c) gout[(size_t)po * l + c] = o[c];
+            }
         }
         if (p.fin.ticket != nullptr) {
             __syncthreads();                          // the accumulators are dead: the epilogue reuses shared memory
             const FinParams<T> fin = p.fin;           // a copy: the kernel parameters themselves stay in the constant bank
-            su2_block_finalize<T>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw);
+            su2_block_finalize<T>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw, su2_grad_width(p));
         }
     }
 }

@@ -371,13 +371,19 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                 tvs[1][u] = reinterpret_cast<const float4*>(g_cos_table)[i];
             }
         }
-        const float* pb = p.pulses + (size_t)b * L * 2;
         for (int i = tid; i < CT; i += NT) {
             const int ic = i < L ? i : L - 1;
             const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
-            const double phi = (double)pb[2 * ic];
-            const double phim = (double)pb[2 * im];
-            const float tau = i < L ? pb[2 * ic + 1] : 0.0f;
+            float ph_c, ta_c, ph_m, ta_m;                   // the stored pulse, or the head applied to its logits
+            su2_pulse_at<float>(p, b, ic, ph_c, ta_c);
+            su2_pulse_at<float>(p, b, im, ph_m, ta_m);
+            if (p.head.pulses_out != nullptr && cblk == 0 && i < L) {
+                p.head.pulses_out[((size_t)b * L + i) * 2] = ph_c;
+                p.head.pulses_out[((size_t)b * L + i) * 2 + 1] = ta_c;
+            }
+            const double phi = (double)ph_c;
+            const double phim = (double)ph_m;
+            const float tau = i < L ? ta_c : 0.0f;
             double sn, cs;
             ::sincos(phi, &sn, &cs);
             fwd4[i] = make_float4((float)cs, (float)sn, tau, 0.0f);
@@ -835,9 +841,8 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
         p.Fsum_part[(size_t)cblk * p.B + b] = tot;
     }
     if constexpr (BWD) {
-        float* gout = p.G_part + ((size_t)cblk * p.B + b) * L * 2;
         const int LC2 = C * 2;
-        for (int i = tid; i < 2 * L; i += NT) {
+        auto col_total = [&](int i) {                      // fixed-order sum of accumulator column i over warps / virtual blocks
             float tot = 0.0f;
 #pragma unroll
             for (int q = 0; q < VB; ++q) {
@@ -849,12 +854,28 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                     tot += a_q[i];                         // chunks are consecutive: flat index == pulse index
                 }
             }
-            gout[i] = (i & 1) ? tot : tot * 0.5f;
+            return tot;
+        };
+        if (p.head.mode == 0) {
+            float* gout = p.G_part + ((size_t)cblk * p.B + b) * L * 2;
+            for (int i = tid; i < 2 * L; i += NT) {
+                const float tot = col_total(i);
+                gout[i] = (i & 1) ? tot : tot * 0.5f;
+            }
+        } else {
+            // head backward: one thread per pulse, (d/dphi, d/dtau) -> the head's input row
+            const int po = su2_grad_width(p);
+            float* gout = p.G_part + ((size_t)cblk * p.B + b) * L * po;
+            for (int l = tid; l < L; l += NT) {
+                float o[3];
+                su2_head_grad<float>(p, b, l, col_total(2 * l) * 0.5f, col_total(2 * l + 1), o);
+                for (int c = 0; c < po; ++c) gout[(size_t)po * l + c] = o[c];
+            }
         }
         if (p.fin.ticket != nullptr) {
             __syncthreads();                               // the accumulators are dead: the epilogue reuses shared memory
             const FinParams<float> fin = p.fin;            // a copy: the kernel parameters themselves stay in the constant bank
-            su2_block_finalize<float>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw);
+            su2_block_finalize<float>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw, su2_grad_width(p));
         }
     }
 }

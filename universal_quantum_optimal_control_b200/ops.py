@@ -27,7 +27,7 @@ from .peer import PeerExchange
 from .sharding import shard_errors, shard_range
 
 __all__ = [
-    "fused_propagate_loss", "propagate_fidelity", "batched_unitary_generator", "fidelity",
+    "fused_propagate_loss", "fused_head_propagate_loss", "propagate_fidelity", "batched_unitary_generator", "fidelity",
     "sharp_loss", "negative_log_loss", "infidelity_loss", "custom_loss",
     "get_ore_ple_error_distribution", "get_ore_error_distribution", "philox_errors",
     "target_coeffs", "tuning_flags", "fp32_peak_tflops",
@@ -387,6 +387,92 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     fl = flags | (FLAG_FAST_SINCOS if fast_sincos else 0)
     return _FusedPropagateLoss.apply(p, tc, error, M, j0, M_total, tuple(float(s) for s in sigma), int(seed), int(offset),
                                      loss, tau, k, fl, group, F_out, err_out, workspace)
+
+
+class _FusedHeadPropagateLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, tc, error, M, sigma, seed, offset, loss, tau, k, flags, mode, ranges, scale, phi_offset, base,
+                pulses_out, F_out, err_out, ws):
+        B, L, P = logits.shape
+        need_grad = ctx.needs_input_grad[0]
+        n_g = B * L * P if need_grad else 0
+        buf = torch.empty(n_g + B, dtype=logits.dtype, device=logits.device)
+        G, Fsum = (buf[:n_g] if need_grad else None), buf[n_g:]
+        loss_out = torch.empty(3, dtype=logits.dtype, device=logits.device)
+        # the workspace rows are sized for the widest gradient row (uqoc_su2_workspace_bytes)
+        n = _su2_ws_bytes(B, L, M, _dt(logits), flags, logits.device)
+        if ws is None:
+            ws = _workspace(n, logits.device)
+        elif ws.numel() < n:
+            raise ValueError(f"workspace of {ws.numel()} bytes is too small for this launch shape ({n} bytes)")
+        rg = (C.c_double * 4)(*ranges)
+        _call("uqoc_su2_head_step", logits.device, _ptr(logits), mode, rg, float(scale), _ptr(phi_offset), _ptr(base), _ptr(tc),
+              _ptr(error), B, L, M, sigma[0], sigma[1], seed, offset, LOSS_KINDS[loss], float(tau), float(k), _ptr(pulses_out),
+              _ptr(F_out), _ptr(err_out), _ptr(Fsum), _ptr(G), _ptr(loss_out), _ptr(ws), n, _dt(logits), flags,
+              _stream(logits.device))
+        mean_fid = Fsum / M
+        if need_grad:
+            ctx.save_for_backward(G.view(B, L, P))
+        ctx.mark_non_differentiable(mean_fid)
+        return loss_out[0], mean_fid
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_mean):
+        (G,) = ctx.saved_tensors
+        return (g_loss * G,) + (None,) * 19
+
+
+def fused_head_propagate_loss(logits: torch.Tensor, U_target: torch.Tensor, *, head: str,
+                              pulse_ranges: Sequence[Sequence[float]], phi_offset: Optional[torch.Tensor] = None,
+                              base_pulse: Optional[torch.Tensor] = None, scale: float = 0.2,
+                              error: Optional[torch.Tensor] = None, monte_carlo: int, sigma: Sequence[float] = (1.0, 0.05),
+                              seed: int = 0, offset: int = 0, loss: str = "sharp", tau: float = 0.99, k: float = 100,
+                              dtype: Optional[torch.dtype] = None, flags: int = 0, pulses_out: Optional[torch.Tensor] = None,
+                              F_out: Optional[torch.Tensor] = None, err_out: Optional[torch.Tensor] = None,
+                              workspace: Optional[torch.Tensor] = None):
+    """:func:`fused_propagate_loss` with the pulse generator's element-wise head folded in:
+    ``logits`` are the raw outputs of the model's last linear layer -- (B, L, 2) for ``head="transformer"``
+    (``model/universal_model.py:126-143``: sigmoid, range map, optional finetune ``base_pulse`` with ``scale``, relu on
+    tau, ``phi_offset`` = target azimuth, wrap) or (B, L, 3) for ``head="grape"`` (``model/GRAPE_model.py:76-89``).  The
+    fused kernel applies the head while it stages the pulse train and the head's backward while it writes the gradient:
+    ``loss.backward()`` delivers ``d loss / d logits`` and no pulses tensor exists in between (``pulses_out`` (B, L, 2)
+    optionally receives the pulses for logging).  Returns ``(loss, mean fidelity per target)``."""
+    if head not in ("transformer", "grape"):
+        raise ValueError(f"unknown head {head!r}; expected 'transformer' or 'grape'")
+    P = 2 if head == "transformer" else 3
+    if logits.ndim != 3 or logits.shape[-1] != P:
+        raise ValueError(f"'logits' must have shape (B, L, {P})")
+    _require_cuda(logits, "logits")
+    if loss not in LOSS_KINDS:
+        raise ValueError(f"unknown loss {loss!r}; expected one of {sorted(LOSS_KINDS)}")
+    rdt = dtype or _real_dtype(logits)
+    B, L, _ = logits.shape
+    if U_target.shape[0] != B:
+        raise ValueError(f"U_target batch {U_target.shape[0]} != logits batch {B}")
+    (lo0, hi0), (lo1, hi1) = pulse_ranges
+    M = int(monte_carlo)
+    if error is not None:
+        _require_cuda(error, "error")
+        if error.shape != (2, B * M):
+            raise ValueError(f"'error' must have shape (2, {B * M}), got {tuple(error.shape)}")
+        error = error.to(rdt).contiguous()
+    off = base = None
+    if head == "transformer":
+        off = None if phi_offset is None else phi_offset.to(logits.device, rdt).contiguous()
+        base = None if base_pulse is None else base_pulse.to(logits.device, rdt).contiguous()
+        if off is not None and off.shape != (B,):
+            raise ValueError(f"'phi_offset' must have shape ({B},)")
+        if base is not None and base.shape != (L, 2):
+            raise ValueError(f"'base_pulse' must have shape ({L}, 2)")
+    elif phi_offset is not None or base_pulse is not None:
+        raise ValueError("the GRAPE head takes no phi_offset / base_pulse")
+    if pulses_out is not None and (pulses_out.shape != (B, L, 2) or pulses_out.dtype != rdt or not pulses_out.is_contiguous()):
+        raise ValueError(f"'pulses_out' must be a contiguous ({B}, {L}, 2) tensor of dtype {rdt}")
+    return _FusedHeadPropagateLoss.apply(logits.to(rdt).contiguous(), raw_target(U_target, rdt), error, M,
+                                         tuple(float(x) for x in sigma), int(seed), int(offset), loss, tau, k,
+                                         int(flags) | FLAG_RAW_TARGET, 0 if head == "transformer" else 1,
+                                         (float(lo0), float(hi0), float(lo1), float(hi1)), scale, off, base, pulses_out, F_out,
+                                         err_out, workspace)
 
 
 class _PropagateFidelity(torch.autograd.Function):

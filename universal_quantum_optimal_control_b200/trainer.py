@@ -115,13 +115,31 @@ class FusedStepMixin:
                 cache[key] = group
         return cache[key]
 
+    fused_head: bool = True                      # models that expose logits()/uqoc_head (heads.Headless*) skip the pulses tensor
+
+    def _head_call(self, U_emb, U_target, spec, loss):
+        """The step with the model's element-wise tail folded into the fused kernel: single GPU,
+        single-qubit models wrapped by ``heads.HeadlessGRAPE`` / ``heads.HeadlessTransformer``.  None: not applicable."""
+        hs = getattr(self.model, "uqoc_head", None)
+        if not self.fused_head or hs is None or self.fused_group is not None or not isinstance(spec, SigmaSpec):
+            return None
+        logits, azimuth = self.model.logits(U_emb)
+        self._fused_step += 1
+        return ops.fused_head_propagate_loss(logits, U_target, head=hs.kind, pulse_ranges=hs.pulse_ranges, phi_offset=azimuth,
+                                             base_pulse=hs.base_pulse if hs.kind == "transformer" else None, scale=hs.scale,
+                                             monte_carlo=self.monte_carlo, sigma=spec.sigma, seed=self.fused_seed,
+                                             offset=self._fused_step, loss=loss, dtype=self.fused_dtype)
+
     def train_epoch(self, U_emb_batch, U_target_batch, error_distribution) -> float:   # trainer.py:58-94
         self.model.train()
         self.optimizer.zero_grad()
         U_emb = U_emb_batch.to(self.device)
         U_target = U_target_batch.to(self.device)
-        pulses = self.model(U_emb)                                  # (B, L, P)
-        loss, _ = self._fused_call(pulses, U_target, error_distribution, self.fused_loss)
+        out = self._head_call(U_emb, U_target, error_distribution, self.fused_loss)
+        if out is None:
+            pulses = self.model(U_emb)                              # (B, L, P)
+            out = self._fused_call(pulses, U_target, error_distribution, self.fused_loss)
+        loss = out[0]
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
         self.optimizer.step()
@@ -132,8 +150,10 @@ class FusedStepMixin:
         self.model.eval()
         U_emb = U_emb_batch.to(self.device)
         U_target = U_target_batch.to(self.device)
-        pulses = self.model(U_emb)
-        mean_fid, _ = self._fused_call(pulses, U_target, error_distribution, "none")     # loss "none" = pooled mean F
+        out = self._head_call(U_emb, U_target, error_distribution, "none")
+        if out is None:
+            out = self._fused_call(self.model(U_emb), U_target, error_distribution, "none")
+        mean_fid = out[0]                                                                # loss "none" = pooled mean F
         return float(mean_fid.item())
 
 
