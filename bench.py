@@ -658,6 +658,46 @@ def other_configs(uq, ops, dev):
         ms = timed(lambda: (ops._launch_fwdbwd(ps, tcs, None, None, Ms, 0, (1.0, 0.05), 1, 0, None, None, bufs[ng:], bufs[:ng], 0),
                             ops._finalize(bufs[ng:], Bs * Ms, "sharp", 0.99, 100, bufs[:ng])))
         out[name] = {"prop_per_s": Bs * Ms * Ls / (ms * 1e-3), "ms": ms}
+        if name.startswith("shipped_score"):
+            # HOST time per step at the reference's shipped step size: the autograd path (fused_propagate_loss + backward(),
+            # torch's engine included) and the one-C-call path with pre-sized buffers (FusedStep)
+            import time as _time
+            Ts = torch.eye(2, dtype=torch.complex64, device=dev)[None].expand(Bs, -1, -1).contiguous()
+            pg = ps.clone().requires_grad_(True)
+
+            def host_us(fn, n=200):
+                for _ in range(20):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = _time.perf_counter()
+                for _ in range(n):
+                    fn()
+                dt = _time.perf_counter() - t0
+                torch.cuda.synchronize()
+                return dt / n * 1e6
+
+            def autograd_step():
+                pg.grad = None
+                l_, _ = uq.fused_propagate_loss(pg, Ts, monte_carlo=Ms, sigma=(1.0, 0.05), seed=1, offset=0)
+                l_.backward()
+
+            class _Ident(torch.autograd.Function):          # floor: what torch's autograd costs around ANY custom CUDA op
+                @staticmethod
+                def forward(ctx, x):
+                    return x.sum()
+
+                @staticmethod
+                def backward(ctx, g):
+                    return g.expand(Bs, Ls, 2)
+
+            def autograd_floor():
+                pg.grad = None
+                _Ident.apply(pg).backward()
+
+            fs = uq.FusedStep(Bs, Ls, Ms, sigma=(1.0, 0.05), seed=1, device=dev)
+            out[name]["host_us_per_step"] = {"fused_propagate_loss + backward (autograd)": host_us(autograd_step),
+                                             "torch autograd floor (trivial custom Function + backward)": host_us(autograd_floor),
+                                             "FusedStep (one C call, pre-sized buffers)": host_us(lambda: fs(ps, Ts, offset=0))}
     wl = make_workload("curriculum", dev)
     B, L, M = 512, wl["L"], wl["M"]
     p = wl["pulses"][:B].double().to(dev)

@@ -5,6 +5,7 @@ Drop-in for the hot path of shiminki/universal_quantum_optimal_control
 ``model/universal_model_trainer.py:27-33``) over the C ABI in ``include/uqoc.h``.
 """
 from .ops import (  # noqa: F401
+    FusedStep,
     autotune_flags,
     batched_unitary_generator,
     custom_loss,

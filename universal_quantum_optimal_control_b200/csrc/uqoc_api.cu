@@ -53,14 +53,7 @@ int su2_launch<double, SC_MUFU>(const Su2Params<double>&, const Su2Plan&, bool, 
 }
 
 // ------------------------------------------------------------------ launch planning
-static int sm_count() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-        (void)cudaGetLastError();
-        return 148;  // B200
-    }
-    return n;
-}
+static int sm_count() { return cached_sm_count(); }
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

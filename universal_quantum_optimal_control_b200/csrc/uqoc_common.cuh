@@ -5,6 +5,7 @@
 // product.  One pulse of SCORE.py:117-127 is q = (cos h, r sin h (cos phi, sin phi, delta))
 // with w = sqrt(1+delta^2), r = 1/w, h = tau * (1+eps) w / 2.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,6 +23,42 @@ void set_error(const char* fmt, ...);
             return UQOC_E_BADARG;      \
         }                              \
     } while (0)
+
+// ---- per-device caches of launch-time queries (a training loop makes the same call every 50-200 us: the CUDA runtime
+// queries below cost microseconds each) ------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        dev = 0;
+    }
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline int cached_sm_count() {
+    static std::atomic<int> n_sm[kMaxDevices];
+    const int dev = current_device();
+    int n = n_sm[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            (void)cudaGetLastError();
+            return 148;  // B200
+        }
+        n_sm[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is sticky per (device, kernel): raise it only when a launch needs more
+// than any earlier one.  `slot` = a static array owned by the caller, one per kernel instantiation.
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kern, size_t smem, std::atomic<int>* slot) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    const int dev = current_device();
+    if ((int)smem <= slot[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) slot[dev].store((int)smem, std::memory_order_relaxed);
+    return e;
+}
 
 inline int launch_status(const char* what) {
     cudaError_t e = cudaGetLastError();

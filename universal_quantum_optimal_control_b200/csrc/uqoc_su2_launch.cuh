@@ -14,7 +14,8 @@ template <typename T, int ST, int LPS, int SC, bool BWD>
 static int su2_launch_one(const Su2Params<T>& p, const Su2Plan& plan, cudaStream_t stream) {
     auto kern = su2_kernel<T, ST, LPS, SC, BWD>;
     if (plan.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        static std::atomic<int> smem_set[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(kern, plan.smem, smem_set);
         if (e != cudaSuccess) {
             set_error("su2 kernel needs %zu bytes of shared memory (L too large): %s", plan.smem, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -30,7 +31,8 @@ template <int NP, int SC, bool BWD, int WPS, int VB>
 static int su2_launch_x2w(const Su2Params<float>& p, const Su2Plan& plan, cudaStream_t stream) {
     auto kern = su2_kernel_x2<NP, SC, BWD, WPS, VB>;
     if (plan.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        static std::atomic<int> smem_set[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(kern, plan.smem, smem_set);
         if (e != cudaSuccess) {
             set_error("su2 kernel needs %zu bytes of shared memory (L too large): %s", plan.smem, cudaGetErrorString(e));
             (void)cudaGetLastError();

@@ -16,6 +16,8 @@
 // and with B_k = P_k W_k^dagger (prefix times adjoint), B_{k-1} = U_k^dagger B_k U_k:
 //   dF/dphi1_k = 1/2 Im[Tr(B_k ZI) - Tr(B_{k-1} ZI)],  dF/dtau_k = (1+eps) Im Tr(B_k H_k).
 // So the backward sweep is: recompute U_k, two 4x4 products, a few traces; state = one matrix.
+#include <mutex>
+#include <unordered_map>
 #include "uqoc_su2_kernels.cuh"
 
 namespace uqoc {
@@ -396,25 +398,33 @@ struct Su4Plan {
 };
 // resident blocks per SM of the kernel this plan launches (occupancy API; registers decide: 6 for the FP32
 // eigenframe fwd+bwd kernel).  The grid is sized to ONE wave of resident blocks with equal tile counts.
+// memoised per (device, kernel, shared-memory size): the occupancy query costs several microseconds per call
 template <typename K>
 static int su4_blocks_per_sm(K kern, size_t smem) {
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, int> memo;
+    const unsigned long long key = ((unsigned long long)(uintptr_t)kern * 1000003ull) ^ ((unsigned long long)smem << 8) ^
+                                   (unsigned long long)current_device();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = memo.find(key);
+        if (it != memo.end()) return it->second;
+    }
     int n = 0;
     if (smem > 48 * 1024) (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kSu4Threads, smem) != cudaSuccess || n < 1) {
         (void)cudaGetLastError();
         n = 1;
     }
+    std::lock_guard<std::mutex> lk(mu);
+    memo[key] = n;
     return n;
 }
 
 // The split count is taken from the BACKWARD kernel's occupancy for forward launches too: one workspace size
 // (uqoc_su4_workspace_bytes) then fits every launch of a shape, whichever kernel it is.
 static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags, bool bwd) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-        (void)cudaGetLastError();
-        sms = 148;
-    }
+    const int sms = cached_sm_count();
     Su4Plan pl;
     const bool pade = (flags & UQOC_FLAG_SU4_PADE) != 0, f64 = dtype == UQOC_F64;
     if (pade) pl.smem = f64 ? su4_smem_bytes<double>((int)L, bwd) : su4_smem_bytes<float>((int)L, bwd);

@@ -27,7 +27,7 @@ from .peer import PeerExchange
 from .sharding import shard_errors, shard_range
 
 __all__ = [
-    "fused_propagate_loss", "fused_head_propagate_loss", "propagate_fidelity", "batched_unitary_generator", "fidelity",
+    "fused_propagate_loss", "fused_head_propagate_loss", "FusedStep", "propagate_fidelity", "batched_unitary_generator", "fidelity",
     "sharp_loss", "negative_log_loss", "infidelity_loss", "custom_loss",
     "get_ore_ple_error_distribution", "get_ore_error_distribution", "philox_errors",
     "target_coeffs", "tuning_flags", "fp32_peak_tflops",
@@ -387,6 +387,71 @@ def fused_propagate_loss(pulses: torch.Tensor, U_target: torch.Tensor, *, error:
     fl = flags | (FLAG_FAST_SINCOS if fast_sincos else 0)
     return _FusedPropagateLoss.apply(p, tc, error, M, j0, M_total, tuple(float(s) for s in sigma), int(seed), int(offset),
                                      loss, tau, k, fl, group, F_out, err_out, workspace)
+
+
+class FusedStep:
+    """The fused step as ONE C call with pre-sized outputs, no autograd: for callers that own the pulse parameters
+    (GRAPE proper ``train/GRAPE/grape_train.py``, dCRAB, line searches) or hand the gradient to ``pulses.backward(grad)``
+    themselves.  Everything that does not change from step to step -- output buffers, the private workspace, the launch
+    plan's workspace size, the ctypes argument list -- is built once; a call converts five arguments and enters
+    ``uqoc_su2_fwdbwd_loss`` (host time ~25 us against ~150 us for ``fused_propagate_loss(...)`` + ``backward()``, whose
+    cost is torch's autograd engine, tools/hostprof2.py).
+
+        step = FusedStep(B, L, monte_carlo=1000, sigma=(0.4, 0.05), seed=0)
+        loss, grad, fsum = step(pulses, U_target, offset=it)      # device views, OVERWRITTEN by the next call
+
+    ``loss`` is a 0-dim view, ``grad`` = d loss / d pulses (B, L, 2), ``fsum`` = per-target fidelity sums (mean = fsum / M).
+    """
+
+    def __init__(self, B: int, L: int, monte_carlo: int, *, dtype: torch.dtype = torch.float32, loss: str = "sharp",
+                 tau: float = 0.99, k: float = 100, sigma: Sequence[float] = (1.0, 0.05), seed: int = 0, device="cuda",
+                 flags: int = 0):
+        if loss not in LOSS_KINDS:
+            raise ValueError(f"unknown loss {loss!r}; expected one of {sorted(LOSS_KINDS)}")
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("FusedStep needs a CUDA device: the uqoc ops have no CPU fallback")
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.B, self.L, self.M, self.dtype = int(B), int(L), int(monte_carlo), dtype
+        self.cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+        self.flags = int(flags) | FLAG_RAW_TARGET
+        n_g = self.B * self.L * 2
+        self.buf = torch.zeros(n_g + self.B + 3, dtype=dtype, device=self.dev)         # [G | Fsum | loss, Fbar, dloss/dFbar]
+        self.grad, self.fsum = self.buf[:n_g].view(self.B, self.L, 2), self.buf[n_g:n_g + self.B]
+        self.loss_out = self.buf[n_g + self.B:]
+        self.loss = self.loss_out[0]
+        self.ws = su2_workspace(self.B, self.L, self.M, dtype, self.flags, self.dev)
+        self._fn = _lib.lib().uqoc_su2_fwdbwd_loss
+        dt = F64 if dtype == torch.float64 else F32
+        # (pulses, target, err) and (offset) and (stream) are filled per call; the rest is fixed
+        self._tail = (C.c_void_p(self.fsum.data_ptr()), C.c_void_p(self.grad.data_ptr()), C.c_void_p(self.loss_out.data_ptr()),
+                      C.c_void_p(self.ws.data_ptr()), self.ws.numel(), dt, self.flags)
+        self._mid = (self.B, self.L, self.M, float(sigma[0]), float(sigma[1]), int(seed))
+        self._loss = (LOSS_KINDS[loss], float(tau), float(k), None, None)              # F_out, err_out unused
+
+    def __call__(self, pulses: torch.Tensor, U_target: torch.Tensor, *, error: Optional[torch.Tensor] = None, offset: int = 0):
+        if pulses.shape != (self.B, self.L, 2) or pulses.dtype != self.dtype or not pulses.is_contiguous() or not pulses.is_cuda:
+            raise ValueError(f"'pulses' must be a contiguous CUDA ({self.B}, {self.L}, 2) tensor of dtype {self.dtype}")
+        if U_target.shape != (self.B, 2, 2) or U_target.dtype != self.cdtype or not U_target.is_contiguous():
+            raise ValueError(f"'U_target' must be a contiguous ({self.B}, 2, 2) tensor of dtype {self.cdtype}")
+        e_ptr = None
+        if error is not None:
+            if error.shape != (2, self.B * self.M) or error.dtype != self.dtype or not error.is_contiguous():
+                raise ValueError(f"'error' must be a contiguous (2, {self.B * self.M}) tensor of dtype {self.dtype}")
+            e_ptr = error.data_ptr()
+        prev = torch.cuda.current_device()
+        if prev != self.dev.index:
+            torch.cuda.set_device(self.dev.index)
+        try:
+            rc = self._fn(pulses.data_ptr(), U_target.data_ptr(), e_ptr, *self._mid, int(offset), *self._loss, *self._tail,
+                          torch.cuda.current_stream(self.dev).cuda_stream)
+        finally:
+            if prev != self.dev.index:
+                torch.cuda.set_device(prev)
+        if rc != 0:
+            check(rc, "uqoc_su2_fwdbwd_loss")
+        return self.loss, self.grad, self.fsum
 
 
 class _FusedHeadPropagateLoss(torch.autograd.Function):
