@@ -228,8 +228,9 @@ def main():
     ap.add_argument("--fast-sincos", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="tuning flags (tuning_flags())")
-    ap.add_argument("--chunks", type=int, default=4,
-                    help="N>1, large exchange vector: target chunks of the pipelined step (all-reduce of chunk n under kernel n+1)")
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="N>1, large exchange vector: target chunks of the pipelined step (all-reduce of chunk n under kernel n+1); "
+                         "0 = wave-sized chunks chosen by PipelinedStep")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="N>1: all-reduce of [Fsum|G] through NCCL, or fused into the partials reduction over NVLink peer "
                          "memory (uqoc_su2_fwdbwd_peer); auto = peer when the vector is small (<= 2^18 reals)")
@@ -281,7 +282,7 @@ def main():
         if args.exchange == "peer" or (B + n_g) <= peer_mod.MAX_N:
             px = uq.PeerExchange(group, B, L, 2, rdt, dev)
     if px is None and err_d is None and (group is not None or args.chunks > 1):
-        pipe = uq.PipelinedStep(B, L, M_total, chunks=max(1, args.chunks), dtype=rdt, sigma=wl["sigma"], seed=1234, group=group,
+        pipe = uq.PipelinedStep(B, L, M_total, chunks=(args.chunks if args.chunks > 0 else "auto"), dtype=rdt, sigma=wl["sigma"], seed=1234, group=group,
                                 device=dev, flags=flags)
     loss_dev = torch.empty(3, dtype=rdt, device=dev)
     launches = {"n": 0}
@@ -383,7 +384,7 @@ def main():
         e2e["GraphedFusedStep"] = wall(lambda i: gs(pulses_h, target_h, err_h))
     # and through the target-chunked pipeline (copies and all-reduce of chunk n under the kernel of chunk n+1)
     if err_h is None and px is None:
-        pe = pipe if pipe is not None else uq.PipelinedStep(B, L, M_total, chunks=4, dtype=rdt, sigma=wl["sigma"], seed=1234,
+        pe = pipe if pipe is not None else uq.PipelinedStep(B, L, M_total, chunks=(args.chunks if args.chunks > 0 else "auto"), dtype=rdt, sigma=wl["sigma"], seed=1234,
                                                             group=group, device=dev, flags=flags)
         e2e["PipelinedStep"] = wall(lambda i: pe(pulses_h, target_h, offset=i))
     clocks = sampler.stop() if rank == 0 else None

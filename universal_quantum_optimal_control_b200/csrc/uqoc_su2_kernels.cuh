@@ -1061,7 +1061,9 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
         }
         __syncthreads();
     }
-    // ---- phase 2: wait for every rank's words of this block's outputs, sum the slots in rank order
+    // ---- phase 2: wait for every rank's words of this block's outputs, sum the slots in rank order.  The first group's
+    // totals stay in registers (the usual case: one group per block); further groups park theirs, unscaled, in G.
+    float first_tot = 0.0f;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long i = g * 32 + x;
         if (y < pp.world) {
@@ -1074,24 +1076,34 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
             float t = red[0][x];
             for (int q = 1; q < pp.world; ++q) t += red[q][x];
             if (s_timeout) t = NAN;
-            if (i < n_g) G[i] = t;                         // unscaled; scaled in place below by the same thread
-            else if (i < n) Fsum[i - n_g] = t;
+            if (g == blockIdx.x) first_tot = t;
+            if (i >= n_g && i < n) Fsum[i - n_g] = t;
+            else if (i < n_g && (kind < 0 || g != blockIdx.x)) G[i] = t;
         }
         __syncthreads();
     }
     if (kind < 0) return;
     // ---- phase 3: pooled mean fidelity from ALL exchanged Fsum words (other blocks' columns included: polled here too,
-    // so no cross-block synchronisation), fixed order -> the same bits in every block and on every rank
+    // so no cross-block synchronisation).  One thread per (target, rank) word -- the polls of a pass are in flight
+    // together -- then a fixed-order sum: the same bits in every block and on every rank.
     {
+        __shared__ float fs[1024];
+        const int tpp = 1024 / pp.world;                       // targets per pass
         double a = 0.0;
-        for (int b = threadIdx.x; b < B; b += 1024) {
-            float t = 0.0f;
-            for (int q = 0; q < pp.world; ++q) {
+        for (int b0 = 0; b0 < B; b0 += tpp) {
+            const int bl = (int)threadIdx.x / pp.world, q = (int)threadIdx.x % pp.world;
+            if (bl < tpp && b0 + bl < B) {
                 float v = 0.0f;
-                if (!ll_wait(mine + (size_t)q * pp.n_pad + n_g + b, pp.epoch, v)) s_timeout = 1;
-                t = (q == 0) ? v : t + v;
+                if (!ll_wait(mine + (size_t)q * pp.n_pad + n_g + b0 + bl, pp.epoch, v)) s_timeout = 1;
+                fs[threadIdx.x] = v;
             }
-            a += (double)t;
+            __syncthreads();
+            if ((int)threadIdx.x < tpp && b0 + (int)threadIdx.x < B) {
+                float t = fs[threadIdx.x * pp.world];
+                for (int q2 = 1; q2 < pp.world; ++q2) t += fs[threadIdx.x * pp.world + q2];
+                a += (double)t;
+            }
+            __syncthreads();
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
@@ -1116,7 +1128,7 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
         const float sc = s_scale;
         for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
             const long long i = g * 32 + x;
-            if (i < n_g) G[i] *= sc;
+            if (i < n_g) G[i] = (g == blockIdx.x ? first_tot : G[i]) * sc;
         }
     }
 }
