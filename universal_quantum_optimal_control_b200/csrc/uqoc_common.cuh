@@ -60,6 +60,23 @@ inline cudaError_t ensure_dynamic_smem(K kern, size_t smem, std::atomic<int>* sl
     return e;
 }
 
+// ---- debug build (-DUQOC_DEBUG_CHECKS, tools/debug_checks.sh): device-side bounds asserts on every shared-memory
+// layout and staging / accumulator index, and epoch tags on the chunk-product exchange between the warps of a block
+// (a stale read = a missing or misplaced barrier traps instead of returning a plausible number).  The pool this code is
+// developed on refuses compute-sanitizer (memcheck / racecheck), so these checks plus the oracle comparisons at small
+// sizes are the race / bounds evidence; they compile to nothing in the shipped library.
+#ifdef UQOC_DEBUG_CHECKS
+#include <cassert>
+#define UQOC_ASSERT(c) assert(c)
+#else
+#define UQOC_ASSERT(c) ((void)0)
+#endif
+__device__ __forceinline__ unsigned dyn_smem_bytes() {
+    unsigned v;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+    return v;
+}
+
 inline int launch_status(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -333,6 +333,7 @@ __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
 // thread's loads are independent 16-byte L2 loads, the column total stays in registers through the exchange and the
 // loss, and G is written once, already scaled.  Fixed summation order everywhere: bit-reproducible, and with a peer
 // exchange bit-identical on every rank (slots are summed in rank order).
+__host__ __device__ inline size_t su2_fin_smem_bytes(int nthr, size_t elem);
 #ifdef UQOC_FIN_INLINE
 #define UQOC_FIN_ATTR __forceinline__
 #else
@@ -365,6 +366,7 @@ __device__ UQOC_FIN_ATTR void su2_block_finalize(const FinParams<T>& f, const T*
     if (tid == 0) { stamp[0] = ts_enter; stamp[1] = now(); }
 #endif
     const int n_g = B * L * po, ncol4 = n_g / 4, ncol = ncol4 + B;
+    UQOC_ASSERT(ncol <= nthr && n_g % 4 == 0 && su2_fin_smem_bytes(nthr, sizeof(T)) <= dyn_smem_bytes());
     int Y = nthr / ncol;                                           // part-lanes per column
     if (Y > parts) Y = parts;
     const int cpp = nthr / Y;                                      // columns per part-lane (>= ncol)
@@ -555,6 +557,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
             double sn, cs;
             ::sincos(phi, &sn, &cs);
             const int row = i + i / C;
+            UQOC_ASSERT(row < LPS * (C + 1) && ic < L && im < L);
             fwd_tab[row] = Row4<T>{(T)cs, (T)sn, tau, (T)0};
             if (BWD) {
                 double sd, cd;
@@ -755,6 +758,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
                 constexpr int DUP = reduce_dup_mask(NV, LPS);
                 if ((lane & DUP) == 0) {
                     T* dst = acc + ((size_t)(warp * LPS + k) * C + (size_t)jb * NB) * 2 + base;
+                    UQOC_ASSERT(base >= 0 && ((size_t)(warp * LPS + k) * C + (size_t)jb * NB) * 2 + base < (size_t)kWarps * LPS * C * 2);
 #pragma unroll
                     for (int m = 0; m < NF; ++m) dst[m] += v[m];
                 }

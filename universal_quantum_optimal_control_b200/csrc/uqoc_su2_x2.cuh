@@ -240,6 +240,7 @@ __device__ __forceinline__ void sincos2_tab_il(F2 tau, const F2 (&kap)[NP], F2 (
         T[2 * u] = f2(__int_as_float(k0 & MASK) * 1e-9f, 1.0f);
         T[2 * u + 1] = f2(__int_as_float(k1 & MASK) * 1e-9f, 1.0f);
 #else
+        UQOC_ASSERT((unsigned)(k0 & MASK) < (unsigned)(FULL ? UQOC_SINCOS_TABLE_LEN : kTabN));
         T[2 * u].v = tsc[k0 & MASK];
         T[2 * u + 1].v = tsc[k1 & MASK];
 #endif
@@ -345,6 +346,9 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
     float* acc = scratch + 32;
     float* xq = acc + acc_len;                              // [kWarps][ST][5][32], WPS > 1 only
 
+    UQOC_ASSERT((size_t)(reinterpret_cast<unsigned char*>(vb_base + (size_t)VB * vb_len) - smem_raw) <= dyn_smem_bytes());
+    UQOC_ASSERT(C % NB == 0 && C >= NB && (long long)C * WPS >= p.L);
+
     const int cblk = blockIdx.x % p.cps;                   // this block among the target's blocks
     const int b = blockIdx.x / p.cps;
     const int split = cblk * VB + vb;                      // sample-tile stream
@@ -386,6 +390,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
             const float tau = i < L ? ta_c : 0.0f;
             double sn, cs;
             ::sincos(phi, &sn, &cs);
+            UQOC_ASSERT(i < CT && ic < L && im < L);
             fwd4[i] = make_float4((float)cs, (float)sn, tau, 0.0f);
             if (BWD) {
                 double sd, cd;
@@ -559,21 +564,28 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
 #pragma unroll
             for (int u = 0; u < ST; ++u) {
                 float* dst = xq + ((size_t)(warp * ST + u) * 5) * 32 + lane;
+                UQOC_ASSERT((size_t)(dst + 128 - xq) < (size_t)xq_len);
                 dst[0] = Pin[u].a; dst[32] = Pin[u].b; dst[64] = Pin[u].c; dst[96] = Pin[u].d;
+#ifdef UQOC_DEBUG_CHECKS
+                dst[128] = __int_as_float((par[u] & 1) | (tile << 1));      // epoch tag: which tile this product belongs to
+#else
                 dst[128] = __int_as_float(par[u] & 1);
+#endif
             }
             vb_sync<VB>(vb);
 #pragma unroll
             for (int u = 0; u < ST; ++u) {
                 const float* s0 = xq + ((size_t)u * 5) * 32 + lane;
                 Quat<float> run{s0[0], s0[32], s0[64], s0[96]};
-                int ptot = __float_as_int(s0[128]);
+                UQOC_ASSERT((__float_as_int(s0[128]) >> 1) == tile);       // a stale slot = a missing barrier
+                int ptot = __float_as_int(s0[128]) & 1;
                 if (warp == 0) Pin[u] = run;
 #pragma unroll
                 for (int w2 = 1; w2 < WPS; ++w2) {
                     const float* sw = xq + ((size_t)(w2 * ST + u) * 5) * 32 + lane;
                     const Quat<float> Qw{sw[0], sw[32], sw[64], sw[96]};
-                    ptot ^= __float_as_int(sw[128]);
+                    UQOC_ASSERT((__float_as_int(sw[128]) >> 1) == tile);
+                    ptot ^= __float_as_int(sw[128]) & 1;
                     run = qmul(Qw, run);                   // later pulses on the left
                     if (w2 == warp) Pin[u] = run;
                 }
@@ -750,6 +762,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                     if ((lane & DUP) == 0) {
                         // WPS = 1: per-warp slice of the whole train;  WPS = 4: this warp's chunk of the train
                         float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
+                        UQOC_ASSERT(base >= 0 && ((size_t)warp * C + (size_t)jb * NB) * 2 + base + NF <= (size_t)acc_len);
 #pragma unroll
                         for (int m = 0; m < NF; ++m) dst[m] += v[m];
                     }
@@ -816,6 +829,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                     constexpr int DUP = reduce_dup_mask(NV, 1);
                     if ((lane & DUP) == 0) {
                         float* dst = acc + ((size_t)warp * C + (size_t)jb * NB) * 2 + base;
+                        UQOC_ASSERT(base >= 0 && ((size_t)warp * C + (size_t)jb * NB) * 2 + base + NF <= (size_t)acc_len);
 #pragma unroll
                         for (int m = 0; m < NF; ++m) dst[m] += v[m];
                     }
