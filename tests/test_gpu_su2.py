@@ -157,14 +157,13 @@ def test_wide_angle_range_negative_and_multi_turn(st, lps, nopk, wps, notab):
     want_l, want_g, want_F = orc.loss_and_grad(pulses.astype(np.float64), T, err.astype(np.float64), M, "infidelity")
     flags = uq.tuning_flags(st=st, lps=lps, no_packed=nopk, wps=wps, no_table=notab)
     val, grad, F, _ = _fused(pulses, T, err, M, torch.float32, loss="infidelity", flags=flags)
-    # Outside BASELINE's tolerance domain on purpose: angles reach ~60 rad here, so the FP32 rounding of the INPUT angle
-    # h itself (6e-8 relative) is 4e-6 rad per pulse -- the bound is input conditioning, not kernel error (the FP64
-    # kernel on the same inputs is checked to 1e-11 below); measured values are recorded
+    # Outside BASELINE's angle domain on purpose (angles reach ~60 rad, so the FP32 rounding of the INPUT angle alone is
+    # 4e-6 rad per pulse), yet still inside north_star's tolerances: measured 4.5e-6 / 2.5e-6 (recorded per run)
     dF = (np.abs(F - want_F) / _fscale(T, B, M)).max()
-    record_measured("test_wide_angle_range_negative_and_multi_turn", "dF/scale", dF, 3e-5, "angles to 60 rad: FP32 input rounding")
-    record_measured("test_wide_angle_range_negative_and_multi_turn", "rel dG", _relerr(grad, want_g), 5e-4, "angles to 60 rad")
-    assert dF < 3e-5
-    assert _relerr(grad, want_g) < 5e-4
+    record_measured("test_wide_angle_range_negative_and_multi_turn", "dF/scale", dF, 1e-5, "angles to 60 rad: FP32 input rounding")
+    record_measured("test_wide_angle_range_negative_and_multi_turn", "rel dG", _relerr(grad, want_g), 1e-4, "angles to 60 rad")
+    assert dF < 1e-5
+    assert _relerr(grad, want_g) < 1e-4
     val64, grad64, F64, _ = _fused(pulses, T, err, M, torch.float64, loss="infidelity", flags=uq.tuning_flags(st=min(st, 2), lps=lps))
     assert np.abs(F64 - want_F).max() < 1e-11
     assert _relerr(grad64, want_g) < 1e-10
@@ -220,8 +219,9 @@ def test_score_composite_pulses(key):
     g = load_golden("score_pulses.npz")
     K = g["probe"].shape[1]
     # FP32: the pulse angles are given in float32 (util.py:64-112) with rotations up to ~12 rad over L ~ 400 segments;
-    # the reference's own complex64 path is 2e-5 off its complex128 path on these pulses
-    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 2e-5)):
+    # the reference's own complex64 path is 2e-5 off its complex128 path on these pulses; the FP32 kernels
+    # stay inside north_star's 1e-5 (measured 2.9e-7)
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 1e-5)):
         pulse = _t(g[f"{key}_pulse"], dtype)
         U = uq.batched_unitary_generator(pulse.expand(K, -1, -1), _t(g["probe"], dtype))
         F = uq.fidelity(U, _t(g[f"{key}_U_target"]).expand(K, -1, -1), 1).cpu().numpy()
@@ -434,9 +434,9 @@ def test_long_pulse_train_uses_opt_in_shared_memory_and_rejects_beyond():
         assert np.abs(F - want_F).max() < 1e-11 and _relerr(grad, want_g) < 1e-10
         val, grad, F, _ = _fused(pulses.astype(np.float32), T, err.astype(np.float32), M, torch.float32, flags=uq.tuning_flags(st=st))
         # 1500 pulses: 6x the longest BASELINE train; FP32 rounding accumulates ~sqrt(L) -- measured values recorded
-        record_measured("test_long_pulse_train", "dF", np.abs(F - want_F).max(), 2e-5, f"L=1500 st={st}")
+        record_measured("test_long_pulse_train", "dF", np.abs(F - want_F).max(), 1e-5, f"L=1500 st={st}")
         record_measured("test_long_pulse_train", "rel dG", _relerr(grad, want_g), 1e-4, f"L=1500 st={st}")
-        assert np.abs(F - want_F).max() < 2e-5 and _relerr(grad, want_g) < 1e-4
+        assert np.abs(F - want_F).max() < 1e-5 and _relerr(grad, want_g) < 1e-4
     big = torch.zeros(1, 60000, 2, device=DEV)
     with pytest.raises(UqocError, match="shared memory"):
         uq.fused_propagate_loss(big.requires_grad_(True), _t(T[:1]), monte_carlo=8)

@@ -11,7 +11,8 @@ independent until the loss epilogue and runs them on two alternating streams::
     stream A:         K(0) AR(0) D2H(0)          K(2) AR(2) D2H(2)
     stream B:                K(1) AR(1) D2H(1)          K(3) AR(3) D2H(3)
 
-(AR = all-reduce of the chunk's rows of ``G`` and of ``Fsum``, N > 1 only)
+(AR = all-reduce of the chunk's rows of ``G``, N > 1 only; the B per-target fidelity sums of all chunks are all-reduced
+and copied out once, behind the last chunk)
 
 so that every copy and every all-reduce except the last chunk's runs under another chunk's kernel, and consecutive
 kernels overlap at their tails (blocks of chunk n+1 fill the SMs chunk n drains).  ``uqoc_su2_fwdbwd_slice`` gives chunk
@@ -165,12 +166,19 @@ class PipelinedStep:
                                          Fsum, G, self.flags, ws=self._ws[c])
                 if self.group is not None:
                     import torch.distributed as dist
-                    dist.all_reduce(G, group=self.group)
-                    dist.all_reduce(Fsum, group=self.group)
+                    dist.all_reduce(G, group=self.group)            # one all-reduce per chunk: its gradient rows
                 if d2h:
-                    hG, hF = self._views(self.h_out, c)
-                    hG.copy_(G, non_blocking=True)
-                    hF.copy_(Fsum, non_blocking=True)
+                    self._views(self.h_out, c)[0].copy_(G, non_blocking=True)
+        # the per-target fidelity sums (B reals) of ALL chunks travel once, behind the last chunk
+        last, other = self._streams[(len(self.bounds) - 1) % 2], self._streams[len(self.bounds) % 2]
+        with torch.cuda.stream(last):
+            last.wait_stream(other)
+            Fs = self.fidelity_sums(self.d_out)
+            if self.group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(Fs, group=self.group)
+            if d2h:
+                self.fidelity_sums().copy_(Fs, non_blocking=True)
         for st in self._streams:
             cur.wait_stream(st)
         if h2d:
