@@ -289,6 +289,27 @@ __device__ __forceinline__ void su2_loss_eval(double Fbar, int kind, double tau,
     }
 }
 
+// FP32 twin for the FP32-only exchange kernel: the double-precision exp / log / divisions above are ~1 us of dependent
+// FP64 latency on the step's critical path there; relative error 1e-7, far inside the FP32 path's own accuracy, and the
+// same on every rank (bit-identical replicas).  Fbar arrives exact (double sum, rounded once).
+__device__ __forceinline__ void su2_loss_eval_f32(float Fbar, int kind, float tau, float k, float& val, float& dval) {
+    if (kind == UQOC_LOSS_SHARP) {
+        const float z = expf(-k * (Fbar - tau));
+        const float lg = log1pf(z);
+        val = lg * (1.0f - Fbar);
+        dval = -k * z / (1.0f + z) * (1.0f - Fbar) - lg;
+    } else if (kind == UQOC_LOSS_NLL) {
+        val = -logf(Fbar);
+        dval = -1.0f / Fbar;
+    } else if (kind == UQOC_LOSS_INFIDELITY) {
+        val = 1.0f - Fbar;
+        dval = -1.0f;
+    } else {
+        val = Fbar;
+        dval = 1.0f;
+    }
+}
+
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1009,18 +1030,29 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 __device__ __forceinline__ bool ll_wait(const unsigned long long* p, unsigned epoch, float& val) {
     unsigned long long w = ld_relaxed_sys_u64(p);
     if ((int)((unsigned)(w >> 32) - epoch) < 0) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        // tight poll; the wall clock (a slow system-level read) is consulted every 4096 polls only
+        unsigned long long t0 = 0, t1;
+        unsigned spins = 0;
         do {
             w = ld_relaxed_sys_u64(p);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 10000000000ull) return false;
+            if ((++spins & 4095u) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t0 == 0) t0 = t1;
+                else if (t1 - t0 > 10000000000ull) return false;
+            }
         } while ((int)((unsigned)(w >> 32) - epoch) < 0);
     }
     val = __uint_as_float((unsigned)w);
     return true;
 }
 
+#ifdef UQOC_LL_TIMING
+// timing build (tools/ll_timing.py): globaltimer stamps in the workspace's ticket area, 128 bytes below the partial rows
+#define UQOC_LL_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    (reinterpret_cast<unsigned long long*>(const_cast<float*>(G_part)) - 16)[k] = t_; } } while (0)
+#else
+#define UQOC_LL_STAMP(k) ((void)0)
+#endif
 template <int YL>   // a template only so that the header can be included by several translation units
 __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* __restrict__ Fsum_part, const float* __restrict__ G_part,
                                                                int splits, int B, long long n_g, const PeerParams<float> pp,
@@ -1038,7 +1070,9 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
     const size_t set_off = (size_t)(pp.epoch & 1u) * pp.world * pp.n_pad;
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pp.data[pp.rank]) + set_off;
     if (threadIdx.x == 0) s_timeout = 0;
+    UQOC_LL_STAMP(0);
     grid_dependency_wait();
+    UQOC_LL_STAMP(1);
     // ---- phase 1: reduce over the sample-tile partials, push {value, epoch} to every rank's slot[rank]
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long i = g * 32 + x;
@@ -1067,13 +1101,25 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
     }
     // ---- phase 2: wait for every rank's words of this block's outputs, sum the slots in rank order.  The first group's
     // totals stay in registers (the usual case: one group per block); further groups park theirs, unscaled, in G.
+    UQOC_LL_STAMP(2);
     float first_tot = 0.0f;
+    __shared__ float fs[1024];
+    // few targets (the usual case here): the warps that poll no column fetch the B x world fidelity-sum words of phase 3
+    // at the same time, so the loss epilogue does not add a second wait
+    const bool fs_prefetch = kind >= 0 && B * pp.world <= 1024 - 32 * pp.world;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long i = g * 32 + x;
         if (y < pp.world) {
             float v = 0.0f;
             if (!ll_wait(mine + (size_t)y * pp.n_pad + i, pp.epoch, v)) s_timeout = 1;
             red[y][x] = v;
+        } else if (fs_prefetch && g == blockIdx.x) {
+            const int idx = (int)threadIdx.x - 32 * pp.world;          // = b * world + q
+            if (idx < B * pp.world) {
+                float v = 0.0f;
+                if (!ll_wait(mine + (size_t)(idx % pp.world) * pp.n_pad + n_g + idx / pp.world, pp.epoch, v)) s_timeout = 1;
+                fs[idx] = v;
+            }
         }
         __syncthreads();
         if (y == 0) {
@@ -1086,22 +1132,24 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
         }
         __syncthreads();
     }
+    UQOC_LL_STAMP(3);
     if (kind < 0) return;
     // ---- phase 3: pooled mean fidelity from ALL exchanged Fsum words (other blocks' columns included: polled here too,
     // so no cross-block synchronisation).  One thread per (target, rank) word -- the polls of a pass are in flight
     // together -- then a fixed-order sum: the same bits in every block and on every rank.
     {
-        __shared__ float fs[1024];
         const int tpp = 1024 / pp.world;                       // targets per pass
         double a = 0.0;
         for (int b0 = 0; b0 < B; b0 += tpp) {
             const int bl = (int)threadIdx.x / pp.world, q = (int)threadIdx.x % pp.world;
-            if (bl < tpp && b0 + bl < B) {
-                float v = 0.0f;
-                if (!ll_wait(mine + (size_t)q * pp.n_pad + n_g + b0 + bl, pp.epoch, v)) s_timeout = 1;
-                fs[threadIdx.x] = v;
+            if (!fs_prefetch) {
+                if (bl < tpp && b0 + bl < B) {
+                    float v = 0.0f;
+                    if (!ll_wait(mine + (size_t)q * pp.n_pad + n_g + b0 + bl, pp.epoch, v)) s_timeout = 1;
+                    fs[threadIdx.x] = v;
+                }
+                __syncthreads();
             }
-            __syncthreads();
             if ((int)threadIdx.x < tpp && b0 + (int)threadIdx.x < B) {
                 float t = fs[threadIdx.x * pp.world];
                 for (int q2 = 1; q2 < pp.world; ++q2) t += fs[threadIdx.x * pp.world + q2];
@@ -1109,25 +1157,33 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
             }
             __syncthreads();
         }
+        // only the first tpp threads hold a non-zero partial: when they all sit in warp 0 (B <= 32) one butterfly does it
+        if (B > 32) {
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-        if (x == 0) fred[y] = a;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < 32; ++w) tot += fred[w];
-            double val, dval;
-            const double Fbar = tot / n_total;
-            su2_loss_eval(Fbar, kind, tau, k, val, dval);
-            s_scale = s_timeout ? NAN : (float)(dval / n_total);
-            if (blockIdx.x == 0 && loss_out != nullptr) {
-                loss_out[0] = s_timeout ? NAN : (float)val;
-                loss_out[1] = (float)Fbar;
-                loss_out[2] = (float)dval;
+            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            if (x == 0) fred[y] = a;
+            __syncthreads();
+            a = (y == 0) ? fred[x] : 0.0;
+        }
+        if (y == 0) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            if (x == 0) {
+                float val, dval;
+                const float inv_n = (float)(1.0 / n_total);
+                const float Fbar = (float)a * inv_n;
+                su2_loss_eval_f32(Fbar, kind, (float)tau, (float)k, val, dval);
+                s_scale = s_timeout ? NAN : dval * inv_n;
+                if (blockIdx.x == 0 && loss_out != nullptr) {
+                    loss_out[0] = s_timeout ? NAN : val;
+                    loss_out[1] = Fbar;
+                    loss_out[2] = dval;
+                }
             }
         }
         __syncthreads();
     }
+    UQOC_LL_STAMP(4);
     if (y == 0) {
         const float sc = s_scale;
         for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -1135,6 +1191,7 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
             if (i < n_g) G[i] = (g == blockIdx.x ? first_tot : G[i]) * sc;
         }
     }
+    UQOC_LL_STAMP(5);
 }
 
 template <typename T>

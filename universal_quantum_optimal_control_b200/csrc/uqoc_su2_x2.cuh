@@ -332,6 +332,9 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
     const int vb_len = 32 + acc_len + xq_len;
 
     const int tid = threadIdx.x;
+#ifdef UQOC_LL_TIMING
+    if (blockIdx.x == 0 && tid == 0 && p.cps > 1) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (reinterpret_cast<unsigned long long*>(p.G_part) - 16)[6] = t_; }
+#endif
 #ifdef UQOC_FIN_TIMING
     if (p.fin.ticket != nullptr && blockIdx.x == 0 && tid == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -891,6 +894,9 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
             const FinParams<float> fin = p.fin;            // a copy: the kernel parameters themselves stay in the constant bank
             su2_block_finalize<float>(fin, p.G_part, p.Fsum_part, p.cps, p.B, p.L, smem_raw, su2_grad_width(p));
         }
+#ifdef UQOC_LL_TIMING
+        if (tid == 0 && p.cps > 1) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax(reinterpret_cast<unsigned long long*>(p.G_part) - 16 + 7, t_); }
+#endif
     }
 }
 
