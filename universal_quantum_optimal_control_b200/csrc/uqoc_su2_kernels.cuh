@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(kThreads) su2_kernel(const Su2Params<T> p) {
     const int b = blockIdx.x / p.splits;
     const int L = p.L;
 
+    grid_dependency_wait();       // launched as a programmatic dependent launch (su2_launch_one): no input is read above
     // ---- stage the target's pulse train: coalesced loads, trig in double, rounded once ----
     {
         for (int i = tid; i < LPS * C; i += kThreads) {

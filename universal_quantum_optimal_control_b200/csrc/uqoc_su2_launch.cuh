@@ -23,7 +23,9 @@ static int su2_launch_one(const Su2Params<T>& p, const Su2Plan& plan, cudaStream
         }
     }
     const unsigned grid = (unsigned)((long long)p.B * plan.cps);
-    kern<<<grid, kThreads, plan.smem, stream>>>(p);
+    // programmatic dependent launch: the blocks may be scheduled while the previous kernel of the stream drains; they
+    // touch no input before griddepcontrol.wait (su2_kernel)
+    launch_dependent(kern, grid, kThreads, plan.smem, stream, p);
     return launch_status("su2_kernel");
 }
 
@@ -40,7 +42,9 @@ static int su2_launch_x2w(const Su2Params<float>& p, const Su2Plan& plan, cudaSt
         }
     }
     const unsigned grid = (unsigned)((long long)p.B * plan.cps);
-    kern<<<grid, kThreads * VB, plan.smem, stream>>>(p);
+    // programmatic dependent launch: block scheduling and the staging of the (immutable) sin/cos tables overlap the tail
+    // of the previous kernel of the stream; nothing else is read before griddepcontrol.wait (su2_kernel_x2)
+    launch_dependent(kern, grid, kThreads * VB, plan.smem, stream, p);
     return launch_status("su2_kernel_x2");
 }
 template <int NP, int SC, bool BWD>

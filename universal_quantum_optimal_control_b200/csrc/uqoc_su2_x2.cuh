@@ -378,6 +378,10 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                 tvs[1][u] = reinterpret_cast<const float4*>(g_cos_table)[i];
             }
         }
+        // everything above read immutable tables only; the previous kernel of the stream (the optimiser step that wrote the
+        // pulses, or the previous step's epilogue still reading the partial rows this kernel will overwrite) must be complete
+        // from here on (the launch is a programmatic dependent launch, su2_launch_x2w)
+        grid_dependency_wait();
         for (int i = tid; i < CT; i += NT) {
             const int ic = i < L ? i : L - 1;
             const int im = (i - 1) < 0 ? 0 : ((i - 1) < L ? (i - 1) : L - 1);
