@@ -7,9 +7,10 @@ kernel they are serial: 0.1 ms of all-reduce and ~1 ms of PCIe traffic per 8.3 m
 (round 1: device scaling 0.988, end-to-end 0.903).  :class:`PipelinedStep` splits the TARGETS into chunks that are
 independent until the loss epilogue and runs them on two alternating streams::
 
-    copies  :  H2D(0) H2D(1) H2D(2) H2D(3)
-    stream A:         K(0) AR(0) D2H(0)          K(2) AR(2) D2H(2)
-    stream B:                K(1) AR(1) D2H(1)          K(3) AR(3) D2H(3)
+    copy in :  H2D(0) H2D(1)      H2D(2)      H2D(3)
+    stream A:         K(0) AR(0)              K(2) AR(2)
+    stream B:                     K(1) AR(1)              K(3) AR(3)
+    copy out:                 D2H(0)      D2H(1)      D2H(2)      D2H(3) D2H(Fsum)
 
 (AR = all-reduce of the chunk's rows of ``G``, N > 1 only; the B per-target fidelity sums of all chunks are all-reduced
 and copied out once, behind the last chunk)
@@ -87,7 +88,10 @@ class PipelinedStep:
         self._ws = [ops.su2_workspace(b1 - b0, L, self.M, dtype, self.flags, self.dev) for b0, b1 in self.bounds]
         self._streams = [torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)]
         self._copy_stream = torch.cuda.Stream(self.dev)                  # all host->device copies, issued up front
+        self._out_stream = torch.cuda.Stream(self.dev)                   # all device->host copies
         self._h2d_done = [torch.cuda.Event() for _ in self.bounds]
+        self._g_done = [torch.cuda.Event() for _ in self.bounds]
+        self._f_done = torch.cuda.Event()
         self._src_pulses, self._src_target = self.h_pulses, self.h_target
         self._step = 0
 
@@ -145,17 +149,21 @@ class PipelinedStep:
     # ------------------------------------------------------------------ the pipeline
     def _enqueue(self, pulses_d, target_raw, offset, *, h2d: bool, d2h: bool):
         cur = torch.cuda.current_stream(self.dev)
-        for st in self._streams:
+        for st in self._streams + [self._copy_stream, self._out_stream]:
             st.wait_stream(cur)
-        if h2d:
-            # every chunk's inputs start moving now, in chunk order, on their own stream: chunk c's kernel waits for its
-            # event only, so the copies of chunks 1.. run under the kernels of the chunks before them
-            self._copy_stream.wait_stream(cur)
+        n = len(self.bounds)
+
+        def copy_in(c):
+            # host->device copies run on their own stream, one chunk ahead of the kernels: chunk c's kernel waits for
+            # its event only, and the host issues chunk c+1's copies after chunk c's kernel launch, not before it
+            b0, b1 = self.bounds[c]
             with torch.cuda.stream(self._copy_stream):
-                for c, (b0, b1) in enumerate(self.bounds):
-                    self.d_pulses[b0:b1].copy_(self._src_pulses[b0:b1], non_blocking=True)
-                    self.d_target[b0:b1].copy_(self._src_target[b0:b1], non_blocking=True)
-                    self._h2d_done[c].record(self._copy_stream)
+                self.d_pulses[b0:b1].copy_(self._src_pulses[b0:b1], non_blocking=True)
+                self.d_target[b0:b1].copy_(self._src_target[b0:b1], non_blocking=True)
+                self._h2d_done[c].record(self._copy_stream)
+
+        if h2d:
+            copy_in(0)
         for c, (b0, b1) in enumerate(self.bounds):
             st = self._streams[c % 2]
             with torch.cuda.stream(st):
@@ -164,13 +172,21 @@ class PipelinedStep:
                 G, Fsum = self._views(self.d_out, c)
                 ops._launch_fwdbwd_slice(pulses_d[b0:b1], target_raw[b0:b1], None, self.M, self.j0, b0, self.sigma, self.seed, offset,
                                          Fsum, G, self.flags, ws=self._ws[c])
+                if h2d and c + 1 < n:
+                    copy_in(c + 1)
                 if self.group is not None:
                     import torch.distributed as dist
                     dist.all_reduce(G, group=self.group)            # one all-reduce per chunk: its gradient rows
                 if d2h:
+                    self._g_done[c].record(st)
+            if d2h:
+                # device->host copies on their own stream too: a compute stream never waits for a copy (under N ranks
+                # copying at once the PCIe rate per rank halves; kernels of later chunks must not queue behind that)
+                with torch.cuda.stream(self._out_stream):
+                    self._out_stream.wait_event(self._g_done[c])
                     self._views(self.h_out, c)[0].copy_(G, non_blocking=True)
         # the per-target fidelity sums (B reals) of ALL chunks travel once, behind the last chunk
-        last, other = self._streams[(len(self.bounds) - 1) % 2], self._streams[len(self.bounds) % 2]
+        last, other = self._streams[(n - 1) % 2], self._streams[n % 2]
         with torch.cuda.stream(last):
             last.wait_stream(other)
             Fs = self.fidelity_sums(self.d_out)
@@ -178,11 +194,13 @@ class PipelinedStep:
                 import torch.distributed as dist
                 dist.all_reduce(Fs, group=self.group)
             if d2h:
+                self._f_done.record(last)
+        if d2h:
+            with torch.cuda.stream(self._out_stream):
+                self._out_stream.wait_event(self._f_done)
                 self.fidelity_sums().copy_(Fs, non_blocking=True)
-        for st in self._streams:
+        for st in self._streams + [self._copy_stream, self._out_stream]:
             cur.wait_stream(st)
-        if h2d:
-            cur.wait_stream(self._copy_stream)
 
     def run_device(self, pulses_d: torch.Tensor, U_target_d: torch.Tensor, offset: Optional[int] = None) -> torch.Tensor:
         """Device-resident inputs: enqueue the chunked step on the current stream's timeline and apply the loss epilogue
