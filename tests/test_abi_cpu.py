@@ -104,3 +104,36 @@ def test_python_flag_words_match_the_header():
     assert lib.uqoc_peer_data_bytes(513, 8, _lib.F32) == 2 * 8 * 544 * 8     # {value, epoch} words: 8 bytes per real
     assert lib.uqoc_peer_flag_bytes(8) == 8 * 1024 * 4
     assert lib.uqoc_peer_data_bytes(0, 8, _lib.F32) == 0
+
+
+def test_new_entry_points_reject_cpu_tensors_and_bad_shapes():
+    """Folded head / single-call step (round 2): reference-style shape errors, no CPU fallback."""
+    from universal_quantum_optimal_control_b200 import ops
+    T = torch.eye(2, dtype=torch.complex64)[None].expand(3, -1, -1)
+    with pytest.raises(ValueError, match=r"must have shape \(B, L, 3\)"):
+        uq.fused_head_propagate_loss(torch.zeros(3, 5, 2), T, head="grape", pulse_ranges=((-3, 3), (0.1, 0.5)), monte_carlo=4)
+    with pytest.raises(ValueError, match="unknown head"):
+        uq.fused_head_propagate_loss(torch.zeros(3, 5, 2), T, head="mlp", pulse_ranges=((-3, 3), (0.1, 0.5)), monte_carlo=4)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        uq.fused_head_propagate_loss(torch.zeros(3, 5, 2), T, head="transformer", pulse_ranges=((-3, 3), (0.1, 0.5)), monte_carlo=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.FusedStep(3, 5, 4, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        uq.su4_unitary_generator(torch.zeros(3, 5, 3), torch.zeros(3, 3))
+
+
+def test_pipelined_step_chunk_bounds_cover_every_target_once():
+    """PipelinedStep.chunk_bounds (pure host logic): contiguous, exhaustive, non-empty chunks for explicit counts, the
+    ramped sizes and the wave-sized automatic choice (148 SMs x 5 blocks = 740 targets per wave)."""
+    from universal_quantum_optimal_control_b200.pipeline import PipelinedStep as P
+    for B in (1, 2, 5, 37, 64, 100, 739, 740, 1500, 2035, 2036, 2500, 4096, 10000):
+        for chunks, ramp in (("auto", True), (1, False), (2, False), (3, True), (4, True), (6, True), (8, False), (50, True)):
+            b = P.chunk_bounds(B, chunks, ramp, 148)
+            assert b[0][0] == 0 and b[-1][1] == B
+            assert all(x1 == y0 for (_, x1), (y0, _) in zip(b, b[1:]))
+            assert all(x1 > x0 for x0, x1 in b)
+            if chunks != "auto":
+                assert len(b) <= max(1, min(chunks, B))
+    sizes = [x1 - x0 for x0, x1 in P.chunk_bounds(4096, "auto", True, 148)]
+    assert sizes[:2] == [185, 370] and sizes[2:6] == [740] * 4 and sizes[-1] < sizes[-2] < 740      # small outer chunks, whole waves inside
+    assert [x1 - x0 for x0, x1 in P.chunk_bounds(4096, 4, False)] == [1024] * 4
