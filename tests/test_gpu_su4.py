@@ -28,10 +28,10 @@ def _case(seed, B, L, M, J=1.0, sd=1.0):
 PADE = [False, True]      # default eigenframe kernel / per-pulse scaling-and-squaring kernel (UQOC_FLAG_SU4_PADE)
 
 
-@pytest.mark.parametrize("pade", PADE)
-@pytest.mark.parametrize("dtype,tolF,tolG", [(torch.float64, 1e-12, 1e-10), (torch.float32, 1e-5, 1e-4)])
-@pytest.mark.parametrize("L,M,splits", [(1, 5, 0), (7, 70, 0), (33, 130, 3), (128, 64, 0), (400, 96, 0)])
-def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits, pade):
+@pytest.mark.parametrize("pade,wps", [(False, 0), (False, 1), (True, 0)])     # wps 0: library plan (train split over the warps
+@pytest.mark.parametrize("dtype,tolF,tolG", [(torch.float64, 1e-12, 1e-10), (torch.float32, 1e-5, 1e-4)])       # for L >= 32 here), 1: never
+@pytest.mark.parametrize("L,M,splits", [(1, 5, 0), (7, 70, 0), (33, 130, 3), (34, 40, 0), (128, 64, 0), (400, 96, 0)])
+def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits, pade, wps):
     B, J = 3, 0.8
     pulses, err, T = _case(L, B, L, M, J)
     if dtype == torch.float32:
@@ -40,7 +40,7 @@ def test_su4_fused_matches_oracle(dtype, tolF, tolG, L, M, splits, pade):
     p = _t(pulses, dtype).requires_grad_(True)
     F = torch.empty(B * M, dtype=dtype, device=DEV)
     loss, mf = uq.fused_propagate_loss_su4(p, _t(T), error=_t(err, dtype), monte_carlo=M, J=J, F_out=F,
-                                           flags=uq.tuning_flags(splits=splits, su4_pade=pade))
+                                           flags=uq.tuning_flags(splits=splits, su4_pade=pade, wps=wps))
     loss.backward()
     assert np.abs(F.cpu().numpy() - want_F).max() < tolF
     assert abs(loss.item() - want_l) < (1e-11 if dtype == torch.float64 else 1e-4) * max(1, abs(want_l))
@@ -270,3 +270,23 @@ def test_su4_graphed_train_step_matches_eager():
         assert abs(lg - loss.item()) < 1e-5 * max(1.0, abs(loss.item())), (it, lg, loss.item())
     for a, b in zip(m_g.parameters(), m_e.parameters()):
         assert torch.allclose(a, b, atol=1e-5)
+
+
+def test_su4_train_split_kernel_equals_one_thread_per_sample_kernel():
+    """BASELINE config 4 regime (one target, many samples, Philox): the train-split kernel (library plan) against the
+    one-sample-per-thread kernel (UQOC_FLAG_WPS1) -- same samples, fidelities to FP32 rounding, gradients to 1e-5 --
+    plus weights, explicit errors and an odd train length whose last warp gets a short chunk."""
+    for B, L, M in ((1, 128, 32768), (2, 37, 1000), (1, 65, 100)):
+        pulses, err, T = _case(7 + L, B, L, M, 1.0)
+        p0 = _t(pulses, torch.float32)
+        out = []
+        for wps in (0, 1):
+            p = p0.clone().requires_grad_(True)
+            F = torch.empty(B * M, dtype=torch.float32, device=DEV)
+            loss, mf = uq.fused_propagate_loss_su4(p, _t(T), monte_carlo=M, sigma=(0.8, 0.05), seed=3, offset=1, F_out=F,
+                                                   flags=uq.tuning_flags(wps=wps))
+            loss.backward()
+            out.append((loss.item(), F.clone(), p.grad.clone()))
+        assert abs(out[0][0] - out[1][0]) < 2e-6 * max(1.0, abs(out[1][0]))
+        assert (out[0][1] - out[1][1]).abs().max().item() < 5e-6
+        assert ((out[0][2] - out[1][2]).abs().max() / out[1][2].abs().max()).item() < 2e-5, (B, L, M)

@@ -233,6 +233,7 @@ __device__ __forceinline__ void philox_su4<double>(uint64_t j, uint32_t b, uint6
 
 }  // namespace uqoc
 #include "uqoc_su4_eig.cuh"
+#include "uqoc_su4_split.cuh"
 namespace uqoc {
 
 constexpr int kSu4Threads = 64;
@@ -395,12 +396,13 @@ __global__ void __launch_bounds__(kSu4Threads) su4_kernel(const Su4Params<T> p) 
 struct Su4Plan {
     int n_tiles, splits;
     size_t smem;
+    int wps;       // 4: pulse train split over the four warps of a 128-thread block (su4e_split_kernel, few samples)
 };
 // resident blocks per SM of the kernel this plan launches (occupancy API; registers decide: 6 for the FP32
 // eigenframe fwd+bwd kernel).  The grid is sized to ONE wave of resident blocks with equal tile counts.
 // memoised per (device, kernel, shared-memory size): the occupancy query costs several microseconds per call
 template <typename K>
-static int su4_blocks_per_sm(K kern, size_t smem) {
+static int su4_blocks_per_sm(K kern, size_t smem, int threads = 64) {
     static std::mutex mu;
     static std::unordered_map<unsigned long long, int> memo;
     const unsigned long long key = ((unsigned long long)(uintptr_t)kern * 1000003ull) ^ ((unsigned long long)smem << 8) ^
@@ -412,7 +414,7 @@ static int su4_blocks_per_sm(K kern, size_t smem) {
     }
     int n = 0;
     if (smem > 48 * 1024) (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kSu4Threads, smem) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) {
         (void)cudaGetLastError();
         n = 1;
     }
@@ -437,6 +439,20 @@ static Su4Plan su4_plan(int64_t B, int64_t L, int64_t M, int dtype, unsigned fla
         else occ = f64 ? su4_blocks_per_sm(su4e_kernel<double, true, false>, smem_b) : su4_blocks_per_sm(su4e_kernel<float, true, false>, smem_b);
     }
     pl.n_tiles = (int)((M + kSu4Threads - 1) / kSu4Threads);
+    pl.wps = 1;
+    // few samples (fewer one-sample-per-thread warps than ~3/4 of the SM sub-partitions): split the pulse train over the
+    // four warps of 128-thread blocks, 32 samples per block (fused fwd+bwd, eigenframe kernel only).  Every warp repeats
+    // the per-sample eigen-decomposition and pays four 4x4 products for its prefix / seed, ~25 % extra work, so at
+    // BASELINE config 4 (1024 warps for 592 sub-partitions) the one-sample-per-thread kernel stays faster (measured
+    // 0.170 vs 0.221 ms) and keeps the default there.
+    if (bwd && !pade && !(flags & UQOC_FLAG_WPS1) && L >= 32 &&
+        ((flags & UQOC_FLAG_WPS4) || B * (int64_t)pl.n_tiles * 2 * 4 <= (int64_t)sms * 4 * 3)) {
+        pl.wps = 4;
+        pl.smem = f64 ? su4s_smem_bytes<double>((int)L) : su4s_smem_bytes<float>((int)L);
+        occ = f64 ? su4_blocks_per_sm(su4e_split_kernel<double, true>, pl.smem, kSu4sThreads)
+                  : su4_blocks_per_sm(su4e_split_kernel<float, true>, pl.smem, kSu4sThreads);
+        pl.n_tiles = (int)((M + 31) / 32);
+    }
     // one wave: at most sms*occ blocks; every block of a target walks `rounds` tiles (the last may walk one less)
     int64_t splits = ((int64_t)sms * occ) / B;
     if (splits < 1) splits = 1;
@@ -492,7 +508,22 @@ static int su4_run(const void* pulses, const void* target, const void* err, cons
             return UQOC_E_UNSUPPORTED;
         }
     }
-    kern<<<(unsigned)(B * pl.splits), kSu4Threads, pl.smem, stream>>>(p);
+    int threads = kSu4Threads;
+    if constexpr (BWD) {
+        if (pl.wps == 4 && cot == nullptr) {
+            kern = su4e_split_kernel<T, true>;
+            threads = kSu4sThreads;
+            if (pl.smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+                if (e != cudaSuccess) {
+                    set_error("su4 kernel needs %zu bytes of shared memory (L too large): %s", pl.smem, cudaGetErrorString(e));
+                    (void)cudaGetLastError();
+                    return UQOC_E_UNSUPPORTED;
+                }
+            }
+        }
+    }
+    kern<<<(unsigned)(B * pl.splits), threads, pl.smem, stream>>>(p);
     int rc = launch_status("su4_kernel");
     if (rc) return rc;
     if (pl.splits > 1 && (Fsum != nullptr || n_g > 0)) {
@@ -510,9 +541,10 @@ extern "C" {
 
 int64_t uqoc_su4_workspace_bytes(int64_t B, int64_t L, int64_t M, int dtype, unsigned flags) {
     if (B < 1 || L < 1 || M < 1) return 0;
-    const Su4Plan pl = su4_plan(B, L, M, dtype, flags, true);
-    if (pl.splits <= 1) return 0;
-    return (int64_t)pl.splits * (B + B * L * 3) * (dtype == UQOC_F64 ? 8 : 4);
+    const Su4Plan pb = su4_plan(B, L, M, dtype, flags, true), pf = su4_plan(B, L, M, dtype, flags, false);
+    const int splits = pb.splits > pf.splits ? pb.splits : pf.splits;     // the train-split plan of fwd+bwd launches differs
+    if (splits <= 1) return 0;
+    return (int64_t)splits * (B + B * L * 3) * (dtype == UQOC_F64 ? 8 : 4);
 }
 
 static int su4_check(int64_t B, int64_t L, int64_t M, int dtype) {
