@@ -93,6 +93,35 @@ __global__ void __launch_bounds__(128) kfwd(int iters, float seed, u64* out) {
     for (int v = 0; v < 4; ++v) z ^= X[v] ^ Y[v];
     if (z == 0x1234567) out[0] = z;
 }
+// the same product with the instructions that read X (then Y) in the first operand slot issued back to back (.reuse)
+__global__ void __launch_bounds__(128) kfwd2(int iters, float seed, u64* out) {
+    u64 X[4], Y[4];
+    float cs[4], a1[4], a2[4], a3[4];
+    for (int v = 0; v < 4; ++v) {
+        X[v] = pk(1.0f, 1e-3f * (threadIdx.x + v)); Y[v] = pk(1e-3f * v, 1e-4f * threadIdx.x);
+        cs[v] = 1.0f - 1e-7f * (threadIdx.x + v + seed); a1[v] = 1e-4f * (threadIdx.x + v); a2[v] = 1e-4f * (threadIdx.x + 2 * v + 1); a3[v] = 1e-5f * (threadIdx.x + 3 * v + 2);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                u64 nX = mul2(X[v], bc(cs[v]));
+                u64 nY = mul2(sgn_pn(X[v]), bc(a2[v]));
+                nY = fma2(swp(X[v]), bc(a3[v]), nY);
+                nX = fma2(swp_np(X[v]), bc(a1[v]), nX);
+                nY = fma2(Y[v], bc(cs[v]), nY);
+                nY = fma2(swp_np(Y[v]), bc(a1[v]), nY);
+                nX = fma2(sgn_np(Y[v]), bc(a2[v]), nX);
+                nX = fma2(swp_nn(Y[v]), bc(a3[v]), nX);
+                X[v] = nX; Y[v] = nY;
+            }
+        }
+    }
+    u64 z = 0;
+    for (int v = 0; v < 4; ++v) z ^= X[v] ^ Y[v];
+    if (z == 0x1234567) out[0] = z;
+}
 // exact backward core of su2_kernel_x2 (two samples per pair, NP = 2), sin/cos and per-pulse values fixed: 38 FFMA2-class + 4 FADD / iter
 __global__ void __launch_bounds__(128) kbwd(int iters, float seed, u64* out) {
     u64 A[2], Bq[2], W3[2], kdl[2], kr[2], kr2[2], kae[2], s2[2], C2[2];
@@ -240,6 +269,8 @@ int main() {
           const double wi = (double)bps * 4 * iters * 2.0 * 16 / 4.0;
           t = timeit([&] { kfwd<<<blocks, 128>>>(iters, 3.f, (u64*)out); });
           printf("blocks/SM=%d forward product replica (32 instr/iter x2)   %.3f ms  %.2f cycles/instr/SMSP\n", bps, t, t * 1e-3 * khz * 1e3 / ((double)bps * iters * 64.0));
+          t = timeit([&] { kfwd2<<<blocks, 128>>>(iters, 3.f, (u64*)out); });
+          printf("blocks/SM=%d forward product, X-then-Y operand order          %.3f ms  %.2f cycles/instr/SMSP\n", bps, t, t * 1e-3 * khz * 1e3 / ((double)bps * iters * 64.0));
           t = timeit([&] { kbwd<<<blocks, 128>>>(iters, 3.f, (u64*)out); });
           printf("blocks/SM=%d backward core replica (38 packed + 4 FADD /iter x2) %.3f ms  %.2f cycles/packed-instr/SMSP\n", bps, t, t * 1e-3 * khz * 1e3 / ((double)bps * iters * 76.0));
           t = timeit([&] { kbwd2<1><<<blocks, 128>>>(iters, 3.f, (u64*)out); });

@@ -289,27 +289,6 @@ __device__ __forceinline__ void su2_loss_eval(double Fbar, int kind, double tau,
     }
 }
 
-// FP32 twin for the FP32-only exchange kernel: the double-precision exp / log / divisions above are ~1 us of dependent
-// FP64 latency on the step's critical path there; relative error 1e-7, far inside the FP32 path's own accuracy, and the
-// same on every rank (bit-identical replicas).  Fbar arrives exact (double sum, rounded once).
-__device__ __forceinline__ void su2_loss_eval_f32(float Fbar, int kind, float tau, float k, float& val, float& dval) {
-    if (kind == UQOC_LOSS_SHARP) {
-        const float z = expf(-k * (Fbar - tau));
-        const float lg = log1pf(z);
-        val = lg * (1.0f - Fbar);
-        dval = -k * z / (1.0f + z) * (1.0f - Fbar) - lg;
-    } else if (kind == UQOC_LOSS_NLL) {
-        val = -logf(Fbar);
-        dval = -1.0f / Fbar;
-    } else if (kind == UQOC_LOSS_INFIDELITY) {
-        val = 1.0f - Fbar;
-        dval = -1.0f;
-    } else {
-        val = Fbar;
-        dval = 1.0f;
-    }
-}
-
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1170,15 +1149,16 @@ __global__ void __launch_bounds__(32 * YL) su2_reduce_exchange_ll(const float* _
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
             if (x == 0) {
-                float val, dval;
-                const float inv_n = (float)(1.0 / n_total);
-                const float Fbar = (float)a * inv_n;
-                su2_loss_eval_f32(Fbar, kind, (float)tau, (float)k, val, dval);
-                s_scale = s_timeout ? NAN : dval * inv_n;
+                // double, like the single-GPU epilogues: the sharp loss amplifies a rounding of Fbar by k = 100, and the
+                // FP32 alternative saves only 0.35 us
+                double val, dval;
+                const double Fbar = a / n_total;
+                su2_loss_eval(Fbar, kind, tau, k, val, dval);
+                s_scale = s_timeout ? NAN : (float)(dval / n_total);
                 if (blockIdx.x == 0 && loss_out != nullptr) {
-                    loss_out[0] = s_timeout ? NAN : val;
-                    loss_out[1] = Fbar;
-                    loss_out[2] = dval;
+                    loss_out[0] = s_timeout ? NAN : (float)val;
+                    loss_out[1] = (float)Fbar;
+                    loss_out[2] = (float)dval;
                 }
             }
         }

@@ -252,15 +252,28 @@ class GraphedTrainStep:
         self.s_loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.s_fid = torch.zeros(B, dtype=torch.float32, device=self.device)
         self._graphs = {}
+        self.fused_head = True                                        # fold a Headless* model's tail into the fused kernel
         self._ws = None                                               # private workspace (its address is captured)
         self._stream = torch.cuda.Stream(self.device)
 
     def _step_body(self, sigma):
         self.d_rng[1] += 1                                            # fresh Philox offset on every replay
-        pulses = self.model(self.s_emb)
-        fn = ops.fused_propagate_loss_su4 if pulses.shape[-1] == 3 else ops.fused_propagate_loss
         kw = dict(monte_carlo=self.M, sigma=sigma, seed=self.d_rng.data_ptr(), loss=self.loss, dtype=self.dtype,
                   flags=self.flags | 8)                               # 8 = UQOC_FLAG_RNG_FROM_DEVICE
+        hs = getattr(self.model, "uqoc_head", None)
+        if hs is not None and self.fused_head:
+            # model wrapped by heads.Headless*: its element-wise tail runs inside the fused kernel (no pulses tensor)
+            logits, azimuth = self.model.logits(self.s_emb)
+            if self._ws is None:
+                self._ws = ops.su2_workspace(logits.shape[0], logits.shape[1], self.M, self.dtype or torch.float32,
+                                             kw["flags"] | ops.FLAG_RAW_TARGET, self.device)
+            loss, fid = ops.fused_head_propagate_loss(logits, self.s_target, head=hs.kind, pulse_ranges=hs.pulse_ranges,
+                                                      phi_offset=azimuth, base_pulse=hs.base_pulse if hs.kind == "transformer" else None,
+                                                      scale=hs.scale, workspace=self._ws, **kw)
+            self._finish_step(loss, fid)
+            return
+        pulses = self.model(self.s_emb)
+        fn = ops.fused_propagate_loss_su4 if pulses.shape[-1] == 3 else ops.fused_propagate_loss
         if self._ws is None:                                          # first warm-up step, outside capture
             if pulses.shape[-1] == 3:
                 self._ws = ops.su4_workspace(pulses.shape[0], pulses.shape[1], self.M, self.dtype or torch.float32, kw["flags"],
@@ -269,6 +282,9 @@ class GraphedTrainStep:
                 self._ws = ops.su2_workspace(pulses.shape[0], pulses.shape[1], self.M, self.dtype or torch.float32,
                                              kw["flags"] | ops.FLAG_RAW_TARGET, self.device)
         loss, fid = fn(pulses, self.s_target, workspace=self._ws, **kw)
+        self._finish_step(loss, fid)
+
+    def _finish_step(self, loss, fid):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
         self.optimizer.step()
