@@ -10,10 +10,10 @@ independent until the loss epilogue and runs them on two alternating streams::
     copy in :  H2D(0) H2D(1)      H2D(2)      H2D(3)
     stream A:         K(0) AR(0)              K(2) AR(2)
     stream B:                     K(1) AR(1)              K(3) AR(3)
-    copy out:                 D2H(0)      D2H(1)      D2H(2)      D2H(3) D2H(Fsum)
+    copy out:                 D2H(0)      D2H(1)      D2H(2)      D2H(3 + Fsum)
 
-(AR = all-reduce of the chunk's rows of ``G``, N > 1 only; the B per-target fidelity sums of all chunks are all-reduced
-and copied out once, behind the last chunk)
+(AR = all-reduce of the chunk's rows of ``G``, N > 1 only; the B per-target fidelity sums of all chunks sit right behind
+the last chunk's rows in the ``[G | Fsum]`` buffer and travel with them: one all-reduce and one copy for both)
 
 so that every copy and every all-reduce except the last chunk's runs under another chunk's kernel, and consecutive
 kernels overlap at their tails (blocks of chunk n+1 fill the SMs chunk n drains).  ``uqoc_su2_fwdbwd_slice`` gives chunk
@@ -91,7 +91,6 @@ class PipelinedStep:
         self._out_stream = torch.cuda.Stream(self.dev)                   # all device->host copies
         self._h2d_done = [torch.cuda.Event() for _ in self.bounds]
         self._g_done = [torch.cuda.Event() for _ in self.bounds]
-        self._f_done = torch.cuda.Event()
         self._src_pulses, self._src_target = self.h_pulses, self.h_target
         self._step = 0
 
@@ -166,6 +165,7 @@ class PipelinedStep:
             copy_in(0)
         for c, (b0, b1) in enumerate(self.bounds):
             st = self._streams[c % 2]
+            is_last = c == n - 1
             with torch.cuda.stream(st):
                 if h2d:
                     st.wait_event(self._h2d_done[c])
@@ -174,6 +174,12 @@ class PipelinedStep:
                                          Fsum, G, self.flags, ws=self._ws[c])
                 if h2d and c + 1 < n:
                     copy_in(c + 1)
+                if is_last:
+                    # the last chunk's gradient rows end where the fidelity sums of ALL chunks begin ([G | Fsum] layout): its
+                    # all-reduce and its copy-out carry both in one transfer -- nothing hides them, so one NCCL call and one
+                    # copy instead of two each on the step's critical path
+                    st.wait_stream(self._streams[(c + 1) % 2])      # the other stream's chunks wrote their fidelity sums
+                    G = self.d_out[b0 * self.L * 2:]
                 if self.group is not None:
                     import torch.distributed as dist
                     dist.all_reduce(G, group=self.group)            # one all-reduce per chunk: its gradient rows
@@ -184,21 +190,7 @@ class PipelinedStep:
                 # copying at once the PCIe rate per rank halves; kernels of later chunks must not queue behind that)
                 with torch.cuda.stream(self._out_stream):
                     self._out_stream.wait_event(self._g_done[c])
-                    self._views(self.h_out, c)[0].copy_(G, non_blocking=True)
-        # the per-target fidelity sums (B reals) of ALL chunks travel once, behind the last chunk
-        last, other = self._streams[(n - 1) % 2], self._streams[n % 2]
-        with torch.cuda.stream(last):
-            last.wait_stream(other)
-            Fs = self.fidelity_sums(self.d_out)
-            if self.group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(Fs, group=self.group)
-            if d2h:
-                self._f_done.record(last)
-        if d2h:
-            with torch.cuda.stream(self._out_stream):
-                self._out_stream.wait_event(self._f_done)
-                self.fidelity_sums().copy_(Fs, non_blocking=True)
+                    (self.h_out[b0 * self.L * 2:] if is_last else self._views(self.h_out, c)[0]).copy_(G, non_blocking=True)
         for st in self._streams + [self._copy_stream, self._out_stream]:
             cur.wait_stream(st)
 
