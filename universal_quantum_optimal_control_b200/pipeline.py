@@ -77,7 +77,8 @@ class PipelinedStep:
         cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
         self.dtype = dtype
         # pinned host staging (static addresses) and device buffers, both laid out [G (B, L, 2) | Fsum (B)]: a chunk is a
-        # contiguous row range of each part (two all-reduces / copies per chunk, all but the last chunk's hidden)
+        # contiguous row range of each part; its gradient rows are exchanged / copied out as soon as its kernel is done, the
+        # fidelity sums of all chunks together with the LAST chunk's rows (they are adjacent)
         self.n_g = B * L * 2
         self.h_pulses = torch.zeros(B, L, 2, dtype=dtype).pin_memory()
         self.h_target = torch.zeros(B, 2, 2, dtype=cdt).pin_memory()
