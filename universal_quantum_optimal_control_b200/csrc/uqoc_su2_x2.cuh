@@ -172,7 +172,21 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
 #ifndef UQOC_X2_BWD_ORDER
 #define UQOC_X2_BWD_ORDER 0      // 1 = reuse-ordered backward core (BWD_FORM 0 / 1 only)
 #endif
-constexpr int kFwdForm = UQOC_X2_FWD_FORM, kBwdForm = UQOC_X2_BWD_FORM, kBwdOrder = UQOC_X2_BWD_ORDER;
+//   UQOC_X2_BWD_CORE  0 = d/dphi accumulated per pulse as Sr B - k1 uu, A' from its own two FMAs (rounds 1-2)
+//                     1 = two identities of the adjoint rotation about the pulse axis n = (1, 0, delta):
+//                         (a) d/dphi of a pulse is the z-torque, W3(before) - W3(after) (expand W3' = C2 W3 - Sr B + delta k1 t
+//                             with k1 (1 + delta^2) = 1 - C2), and z is untouched by the frame change between pulses, so the
+//                             sample sum telescopes: only S_i = sum_s W3_s entering pulse i is accumulated (one FADD2 per
+//                             pulse instead of four three-register FFMA2) and d/dphi_i = (S_i - S_{i-1}) / 2 is formed once
+//                             per block in the epilogue (S_{-1}: the sweep's exit value, kept per warp);
+//                         (b) the axis component t = A + delta W3 is invariant, so A' = t - delta W3' (one FFMA2 for two).
+//                         19 -> 16.5 FMA-pipe instructions per sample pair and pulse in the backward core.
+#ifndef UQOC_X2_BWD_CORE
+#define UQOC_X2_BWD_CORE 1
+#endif
+constexpr int kFwdForm = UQOC_X2_FWD_FORM, kBwdForm = UQOC_X2_BWD_FORM, kBwdOrder = UQOC_X2_BWD_ORDER, kBwdCore = UQOC_X2_BWD_CORE;
+static_assert(kBwdCore == 0 || (kBwdForm <= 1 && kBwdOrder == 0), "the telescoped backward core exists for the two-samples-per-pair sweep only");
+constexpr int kExitSlot = 8;          // scratch[kExitSlot + warp]: sum over this warp's samples of W3 leaving its sweep (kBwdCore = 1)
 // table entries staged for a kernel: interleaved {sin, cos} pairs and / or separate sin[] / cos[] arrays
 constexpr int x2_tab_il(bool table, bool bwd) {
     return !table ? 0 : ((bwd && kBwdForm >= 1) ? UQOC_SINCOS_TABLE_LEN : ((kFwdForm == 1) ? kTabN : 0));
@@ -407,6 +421,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
         }
         if (BWD) {
             for (int i = vt; i < acc_len; i += kThreads) acc[i] = 0.0f;
+            if (vt < 32) scratch[vt] = 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < TVI; ++u) {
@@ -721,6 +736,42 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                                 A[u] = fma2(B1[u], nsd, tA);
                                 Bq[u] = fma2(B1[u], cd, tB);
                             }
+                        } else if constexpr (kBwdCore == 1) {
+                            // S_i: the z-components entering this pulse, summed over the thread's samples
+                            gp = W3[0];
+#pragma unroll
+                            for (int u = 1; u < NP; ++u) gp = add2(gp, W3[u]);
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                t[u] = fma2(kdl[u], W3[u], A[u]);
+                                uu[u] = fma2(kdl[u], A[u], neg2(W3[u]));
+                            }
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                Sr[u] = mul2(s2[u], kr[u]);
+                                gt = fma2(kae[u], t[u], gt);
+                            }
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                k1_[u] = fma2(neg2(C2[u]), kr2[u], kr2[u]);
+                                BS[u] = mul2(Bq[u], Sr[u]);
+                                B1[u] = mul2(Bq[u], C2[u]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                K[u] = mul2(k1_[u], t[u]);
+                                B1[u] = fma2(neg2(uu[u]), Sr[u], B1[u]);
+                                Wz[u] = fma2(W3[u], C2[u], neg2(BS[u]));
+                            }
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) W3[u] = fma2(kdl[u], K[u], Wz[u]);
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) A1[u] = fma2(neg2(kdl[u]), W3[u], t[u]);     // t is invariant
+#pragma unroll
+                            for (int u = 0; u < NP; ++u) {
+                                A[u] = fma2(neg2(B1[u]), sd, mul2(A1[u], cd));
+                                Bq[u] = fma2(B1[u], cd, mul2(A1[u], sd));
+                            }
                         } else {
 #pragma unroll
                             for (int u = 0; u < NP; ++u) {
@@ -773,6 +824,16 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
 #pragma unroll
                         for (int m = 0; m < NF; ++m) dst[m] += v[m];
                     }
+                }
+                if constexpr (kBwdCore == 1) {
+                    // S_{-1} of this warp's sweep: what its samples' z-components are after the sweep's first pulse
+                    F2 ex = W3[0];
+#pragma unroll
+                    for (int u = 1; u < NP; ++u) ex = add2(ex, W3[u]);
+                    float e1 = f2lo(ex) + f2hi(ex);
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) e1 += __shfl_xor_sync(0xffffffffu, e1, d);
+                    if (lane == 0) scratch[kExitSlot + warp] += e1;
                 }
             } else {
                 // per sample: Z = (A, W3) as one register pair, Bq as a scalar.
@@ -877,19 +938,40 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
             }
             return tot;
         };
+        auto dphi_total = [&](int l) {                     // d/dphi of pulse l (before the factor 1/2)
+            if constexpr (kBwdCore == 0) {
+                return col_total(2 * l);
+            } else {
+                // telescoped z-torque: S_l - S_{l-1}; below the first pulse of a sweep, the sweep's exit sum
+                const bool first = (WPS == 1) ? (l == 0) : (l % C == 0);
+                float prev = 0.0f;
+                if (first) {
+#pragma unroll
+                    for (int q = 0; q < VB; ++q) {
+                        const float* s_q = vb_base + (size_t)q * vb_len + kExitSlot;
+                        if constexpr (WPS == 1) {
+#pragma unroll
+                            for (int w = 0; w < kWarps; ++w) prev += s_q[w];
+                        } else {
+                            prev += s_q[l / C];
+                        }
+                    }
+                } else {
+                    prev = col_total(2 * l - 2);
+                }
+                return col_total(2 * l) - prev;
+            }
+        };
         if (p.head.mode == 0) {
             float* gout = p.G_part + ((size_t)cblk * p.B + b) * L * 2;
-            for (int i = tid; i < 2 * L; i += NT) {
-                const float tot = col_total(i);
-                gout[i] = (i & 1) ? tot : tot * 0.5f;
-            }
+            for (int i = tid; i < 2 * L; i += NT) gout[i] = (i & 1) ? col_total(i) : dphi_total(i >> 1) * 0.5f;
         } else {
             // head backward: one thread per pulse, (d/dphi, d/dtau) -> the head's input row
             const int po = su2_grad_width(p);
             float* gout = p.G_part + ((size_t)cblk * p.B + b) * L * po;
             for (int l = tid; l < L; l += NT) {
                 float o[3];
-                su2_head_grad<float>(p, b, l, col_total(2 * l) * 0.5f, col_total(2 * l + 1), o);
+                su2_head_grad<float>(p, b, l, dphi_total(l) * 0.5f, col_total(2 * l + 1), o);
                 for (int c = 0; c < po; ++c) gout[(size_t)po * l + c] = o[c];
             }
         }
