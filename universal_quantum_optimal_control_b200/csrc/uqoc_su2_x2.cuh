@@ -186,6 +186,21 @@ __device__ __forceinline__ void sincos2_n(const F2 (&h)[NP], F2 (&s)[NP], F2 (&c
 #endif
 constexpr int kFwdForm = UQOC_X2_FWD_FORM, kBwdForm = UQOC_X2_BWD_FORM, kBwdOrder = UQOC_X2_BWD_ORDER, kBwdCore = UQOC_X2_BWD_CORE;
 static_assert(kBwdCore == 0 || (kBwdForm <= 1 && kBwdOrder == 0), "the telescoped backward core exists for the two-samples-per-pair sweep only");
+//   UQOC_X2_IDX3      three-instruction table-index arithmetic on the shifted-node tables (g_*_table_sh,
+//                     tools/gen_sincos_table.py): kf = fma(tau, a N/pi, M3), kc = fma(kf, pi/N, -C0) = (pi/N) k + e0 with ONE
+//                     rounding, r = fma(tau, a, -kc): the residual comes out in radians and the multiplication of the
+//                     index-unit residual by pi/N (one FMUL2 per sample pair and pulse) disappears.  The rounding of kc
+//                     (half an ulp of the ANGLE) is an extra, per-pulse random angle error of the size of the slope's own
+//                     rounding.  Bit 0 = forward sweep, bit 1 = backward sweep.  Measured on the bench launch (4096
+//                     targets x 4096 samples x L = 256) and the GPU suite (profiles/r2_bwd_core_identities.txt):
+//                       0  neither         7.84 ms   max |dF| 2.9e-6 (L = 256 sweep), 8.8e-6 (worst case of the suite)
+//                       2  backward only   7.81 ms   the same F bit for bit; rel dG 1.2e-6 (bound 1e-4)
+//                       3  both (default)  7.69 ms   max |dF| 3.3e-6 / 9.4e-6 (bound 1e-5), rel dG 1.1e-6
+//                     Build with -DUQOC_X2_IDX3=2 for the exact forward residual (kf, M - kf, fma, * pi/N, plain tables).
+#ifndef UQOC_X2_IDX3
+#define UQOC_X2_IDX3 3
+#endif
+constexpr bool kIdx3Fwd = (UQOC_X2_IDX3 & 1) != 0, kIdx3Bwd = (UQOC_X2_IDX3 & 2) != 0;
 constexpr int kExitSlot = 8;          // scratch[kExitSlot + warp]: sum over this warp's samples of W3 leaving its sweep (kBwdCore = 1)
 // table entries staged for a kernel: interleaved {sin, cos} pairs and / or separate sin[] / cos[] arrays
 constexpr int x2_tab_il(bool table, bool bwd) {
@@ -202,11 +217,11 @@ constexpr int x2_tab_sep(bool table, bool bwd) {
 // exact (the backward sweep looks up the DOUBLE angle 2h this way); otherwise k mod N and the common sign
 // (-1)^(k div N) is dropped (kb returns k >> 10 so the U_out kernel can track it).
 // Separate sin[] / cos[] arrays, two samples per register pair throughout:
-template <int NP, bool FULL>
-__device__ __forceinline__ void sincos2_tab_sep(F2 tau, const F2 (&kap)[NP], F2 (&s)[NP], F2 (&c)[NP], int (&kb)[2 * NP],
-                                                const float* __restrict__ tsin, const float* __restrict__ tcos) {
+template <int NP, bool FULL, bool kIdx3>
+__device__ __forceinline__ void sincos2_tab_sep(F2 tau, const F2 (&kap)[NP], const F2 (&kar)[NP], F2 (&s)[NP], F2 (&c)[NP],
+                                                int (&kb)[2 * NP], const float* __restrict__ tsin, const float* __restrict__ tcos) {
     constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
-    const float MAGIC = 12582912.0f;
+    const float MAGIC = kIdx3 ? UQOC_SINCOS_M3 : 12582912.0f;
     F2 kf[NP], fr[NP], st[NP], ct[NP];
 #pragma unroll
     for (int u = 0; u < NP; ++u) kf[u] = fma2(tau, kap[u], f2b(MAGIC));
@@ -219,12 +234,20 @@ __device__ __forceinline__ void sincos2_tab_sep(F2 tau, const F2 (&kap)[NP], F2 
         st[u] = f2(tsin[i0], tsin[i1]);
         ct[u] = f2(tcos[i0], tcos[i1]);
     }
+    if constexpr (kIdx3 == 1) {
+        // kar = the slope in radians: r = tau a - ((pi/N) k + e0), the nodes of the shifted tables
 #pragma unroll
-    for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
+        for (int u = 0; u < NP; ++u) kf[u] = fma2(kf[u], f2b(UQOC_SINCOS_STEP), f2b(-UQOC_SINCOS_C0));
 #pragma unroll
-    for (int u = 0; u < NP; ++u) fr[u] = fma2(tau, kap[u], kf[u]);
+        for (int u = 0; u < NP; ++u) fr[u] = fma2(tau, kar[u], neg2(kf[u]));
+    } else {
 #pragma unroll
-    for (int u = 0; u < NP; ++u) fr[u] = mul2(fr[u], f2b(0.0030679615757712823f));
+        for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) fr[u] = fma2(tau, kap[u], kf[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) fr[u] = mul2(fr[u], f2b(0.0030679615757712823f));
+    }
 #pragma unroll
     for (int u = 0; u < NP; ++u) {
         s[u] = fma2(fr[u], ct[u], st[u]);
@@ -234,11 +257,11 @@ __device__ __forceinline__ void sincos2_tab_sep(F2 tau, const F2 (&kap)[NP], F2 
 // INTERLEAVED {sin, cos} table (one LDS.64 per sample); the residual step is done per SAMPLE on the loaded component
 // pair V = (st, ct):  V' = V + (-r) (-ct, st)  -- one FFMA2 whose multiplier rides in the 32-bit broadcast slot and whose
 // other two sources are the SAME register pair (a swap / sign modifier apart).  Outputs V[v] = (sin, cos), v = 2u + half.
-template <int NP, bool FULL>
-__device__ __forceinline__ void sincos2_tab_il(F2 tau, const F2 (&kap)[NP], F2 (&V)[2 * NP], int (&kb)[2 * NP],
-                                               const u64* __restrict__ tsc) {
+template <int NP, bool FULL, bool kIdx3>
+__device__ __forceinline__ void sincos2_tab_il(F2 tau, const F2 (&kap)[NP], const F2 (&kar)[NP], F2 (&V)[2 * NP],
+                                               int (&kb)[2 * NP], const u64* __restrict__ tsc) {
     constexpr int MASK = FULL ? (2 * kTabN - 1) : (kTabN - 1);
-    const float MAGIC = 12582912.0f;
+    const float MAGIC = kIdx3 ? UQOC_SINCOS_M3 : 12582912.0f;
     F2 kf[NP], nr[NP], T[2 * NP];
 #pragma unroll
     for (int u = 0; u < NP; ++u) kf[u] = fma2(tau, kap[u], f2b(MAGIC));
@@ -259,12 +282,19 @@ __device__ __forceinline__ void sincos2_tab_il(F2 tau, const F2 (&kap)[NP], F2 (
         T[2 * u + 1].v = tsc[k1 & MASK];
 #endif
     }
+    if constexpr (kIdx3 == 1) {
 #pragma unroll
-    for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
+        for (int u = 0; u < NP; ++u) kf[u] = fma2(kf[u], f2b(UQOC_SINCOS_STEP), f2b(-UQOC_SINCOS_C0));   // (pi/N) k + e0
 #pragma unroll
-    for (int u = 0; u < NP; ++u) nr[u] = fma2(tau, kap[u], kf[u]);
+        for (int u = 0; u < NP; ++u) nr[u] = fma2(tau, neg2(kar[u]), kf[u]);                             // -r
+    } else {
 #pragma unroll
-    for (int u = 0; u < NP; ++u) nr[u] = mul2(nr[u], f2b(-0.0030679615757712823f));    // -r = -frac * pi/N
+        for (int u = 0; u < NP; ++u) kf[u] = sub2(f2b(MAGIC), kf[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) nr[u] = fma2(tau, kap[u], kf[u]);
+#pragma unroll
+        for (int u = 0; u < NP; ++u) nr[u] = mul2(nr[u], f2b(-0.0030679615757712823f));    // -r = -frac * pi/N
+    }
 #pragma unroll
     for (int u = 0; u < NP; ++u) {
         V[2 * u] = fma2(swp2_np(T[2 * u]), f2b(f2lo(nr[u])), T[2 * u]);                 // (st + r ct, ct - r st)
@@ -332,6 +362,11 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
     const int C = p.C;                 // pulses per chunk (multiple of NB)
     const int CT = C * WPS;            // staged rows
     constexpr int TIL = x2_tab_il(SC == SC_TABLE, BWD), TSEP = x2_tab_sep(SC == SC_TABLE, BWD);   // table entries staged
+    // which sweep reads which staged table decides its node set (plain k pi/N or shifted, see UQOC_X2_IDX3)
+    constexpr bool kIlBwd = BWD && kBwdForm >= 1, kIlFwd = kFwdForm == 1, kSepBwd = BWD && kBwdForm == 0, kSepFwd = kFwdForm == 0;
+    static_assert(!(kIlBwd && kIlFwd) || kIdx3Fwd == kIdx3Bwd, "one interleaved table serves both sweeps: same node set");
+    static_assert(!(kSepBwd && kSepFwd) || kIdx3Fwd == kIdx3Bwd, "one sin[] / cos[] table serves both sweeps: same node set");
+    constexpr bool kIlShift = kIlBwd ? kIdx3Bwd : kIdx3Fwd, kSepShift = kSepBwd ? kIdx3Bwd : kIdx3Fwd;
     // layout: [{sin, cos} pairs @ 0][fwd rows][bwd rows][sin[] | cos[]][per virtual block: scratch, acc, xq].  The separate
     // tables sit BEHIND the run-time sized rows on purpose: ptxas then addresses them as [R + UR + imm]; at a
     // compile-time offset it materialises the base in a vector register and adds it per look-up (+4 % on the step)
@@ -382,14 +417,14 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
 #pragma unroll
         for (int u = 0; u < TVI; ++u) {
             const int i = tid + u * NT;
-            if (i < TIL / 2) tvi[u] = reinterpret_cast<const float4*>(g_sincos_table)[i];
+            if (i < TIL / 2) tvi[u] = reinterpret_cast<const float4*>(kIlShift ? g_sincos_table_sh : g_sincos_table)[i];
         }
 #pragma unroll
         for (int u = 0; u < TVS; ++u) {
             const int i = tid + u * NT;
             if (i < TSEP / 4) {
-                tvs[0][u] = reinterpret_cast<const float4*>(g_sin_table)[i];
-                tvs[1][u] = reinterpret_cast<const float4*>(g_cos_table)[i];
+                tvs[0][u] = reinterpret_cast<const float4*>(kSepShift ? g_sin_table_sh : g_sin_table)[i];
+                tvs[1][u] = reinterpret_cast<const float4*>(kSepShift ? g_cos_table_sh : g_cos_table)[i];
             }
         }
         // everything above read immutable tables only; the previous kernel of the stream (the optimiser step that wrote the
@@ -447,6 +482,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
     for (int tile = split; tile < p.n_tiles; tile += p.splits) {
         // ---- per-sample constants; the table-index slopes ride two SAMPLES per register pair (pair u = samples 2u, 2u+1)
         F2 ka[NP], ka2[NP];      // half / full angle per unit tau: table-index slopes (SC_TABLE) or radians
+        F2 kar[NP], kar2[NP];    // the same slopes in radians (SC_TABLE: the residual of the three-instruction index arithmetic)
         F2 kr[NP], kr2[NP], kdl[NP], kae[NP];   // two-samples-per-pair constants
         F2 RD[ST];               // per sample (1/w, delta/w): (s', q3) = sin h * RD
         float kdl_s[ST], kr_s[ST], kr2_s[ST], kae_s[ST];
@@ -483,6 +519,8 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                     ka[u] = f2(kc[2 * u].a, kc[2 * u + 1].a);
                     ka2[u] = f2(kc[2 * u].a2, kc[2 * u + 1].a2);
                 }
+                kar[u] = f2(kc[2 * u].a, kc[2 * u + 1].a);
+                kar2[u] = f2(kc[2 * u].a2, kc[2 * u + 1].a2);
                 kr[u] = f2(kc[2 * u].r, kc[2 * u + 1].r);
                 kr2[u] = f2(kc[2 * u].r2, kc[2 * u + 1].r2);
                 kdl[u] = f2(kc[2 * u].delta, kc[2 * u + 1].delta);
@@ -511,7 +549,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                 const F2 cc = f2b(row.x), ss = f2b(row.y);
                 F2 h[NP], sn[NP], c[NP], sp[NP], q1[NP], q2[NP], q3[NP];
                 if constexpr (SC == SC_TABLE) {
-                    sincos2_tab_sep<NP, false>(tau, ka, sn, c, kb, tsin, tcos);
+                    sincos2_tab_sep<NP, false, kIdx3Fwd>(tau, ka, kar, sn, c, kb, tsin, tcos);
                 } else {
 #pragma unroll
                     for (int u = 0; u < NP; ++u) h[u] = mul2(tau, ka[u]);
@@ -537,7 +575,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                 // (s', q3) = sin h (1/w, delta/w), (q1, q2) = s' (cos phi, sin phi)
                 const F2 CS = f2(row.x, row.y);
                 F2 V[ST], SQ[ST], Q12[ST];
-                sincos2_tab_il<NP, false>(tau, ka, V, kb, tsc);
+                sincos2_tab_il<NP, false, kIdx3Fwd>(tau, ka, kar, V, kb, tsc);
 #pragma unroll
                 for (int v = 0; v < ST; ++v) SQ[v] = mul2(RD[v], f2b(f2lo(V[v])));
 #pragma unroll
@@ -689,10 +727,10 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                         int kb[ST];
                         if constexpr (SC == SC_TABLE && kBwdForm == 0) {
                             // (sin 2h, cos 2h) straight from the full-period table
-                            sincos2_tab_sep<NP, true>(tau, ka2, s2, C2, kb, tsin, tcos);
+                            sincos2_tab_sep<NP, true, kIdx3Bwd>(tau, ka2, kar2, s2, C2, kb, tsin, tcos);
                         } else if constexpr (SC == SC_TABLE) {
                             F2 V2[ST];                      // per sample on the interleaved pair, then re-paired
-                            sincos2_tab_il<NP, true>(tau, ka2, V2, kb, tsc);
+                            sincos2_tab_il<NP, true, kIdx3Bwd>(tau, ka2, kar2, V2, kb, tsc);
 #pragma unroll
                             for (int u = 0; u < NP; ++u) {
                                 s2[u] = f2(f2lo(V2[2 * u]), f2lo(V2[2 * u + 1]));
@@ -856,7 +894,7 @@ __global__ void __launch_bounds__(kThreads * VB, x2_min_blocks(NP, SC, WPS, VB))
                         const F2 tau = f2b(row.z);
                         F2 V2[ST];                         // (sin 2h, cos 2h)
                         int kb[ST];
-                        sincos2_tab_il<NP, true>(tau, ka2, V2, kb, tsc);
+                        sincos2_tab_il<NP, true, kIdx3Bwd>(tau, ka2, kar2, V2, kb, tsc);
                         float gp = 0.0f, gt = 0.0f;
                         F2 T2[ST], Yk[ST], Z1[ST];
                         float Sr[ST], k1[ST], B1[ST];
